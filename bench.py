@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the merge-based CsrMV path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--values ones|random]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU OmpMergeCsrmv, same config
+
+A *step* is one y = A*x over the whole synthetic matrix through the C ABI (mspmv_csrmv_*), the
+same unit the reference's timed loop repeats (gpu_spmv.cu:421-432).  Metric: GFLOP/s = 2*nnz/t
+(gpu_spmv.cu:455,463).  At N=1 the default workload is BASELINE.json configs[1]: fp64, 1M x 1M,
+64 nnz/row (826 MB of compulsory traffic per step, larger than the 126 MB L2, so no L2 flush is
+needed between steps).  At N>1 the default is the same family grown with N (weak scaling: N*1M
+rows, one merge-path shard per GPU, one all_gather of N carries per step); fixed-size workloads
+(--workload powerlaw_20m ...) are sharded the same way and reported as "strong".
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "csr_spmv_gflops"
+UNIT = "GFLOP/s"
+
+
+# --------------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------------
+def workload_spec(name, n_gpus):
+    """-> (kind, torch dtype, params dict, scaling, description)"""
+    from merge_spmv_b200 import generators as gen
+
+    if name == "default":
+        name = "uniform_1m_64"
+    kind, dt, p = gen.CONFIGS[name]
+    p = dict(p)
+    scaling = "weak"
+    if name == "uniform_1m_64" and n_gpus > 1:
+        p["rows"] *= n_gpus
+        p["cols"] *= n_gpus
+    elif n_gpus > 1:
+        scaling = "strong"
+    return name, kind, dt, p, scaling
+
+
+def build_row_offsets(kind, p):
+    from merge_spmv_b200 import generators as gen
+
+    if kind == "uniform":
+        return gen.uniform_row_offsets(p["rows"], p["nnz_per_row"]), p["cols"], None
+    if kind == "powerlaw":
+        lengths, alpha = gen.powerlaw_row_lengths(p["rows"], min(p["max_row"], p["cols"]), p["target_nnz"])
+        return gen._offsets_from_lengths(lengths), p["cols"], alpha
+    return gen.banded_row_offsets(p["rows"], p["half_bandwidth"]), p["rows"], None
+
+
+def fill(kind, row_offsets, cols, k0, k1, dt, values, device, p):
+    from merge_spmv_b200 import generators as gen
+
+    return gen.fill_nonzeros(row_offsets, cols, k0, k1, kind="banded" if kind == "banded" else "stratified",
+                             dtype=dt, values=values, device=device,
+                             half_bandwidth=p.get("half_bandwidth", 3),
+                             seed={"uniform": 0x5EED0001, "powerlaw": 0x5EED0003, "banded": 0x5EED0004}[kind])
+
+
+def algorithmic_bytes(rows, cols, nnz, vb):
+    # every array once
+    return nnz * (vb + 4) + (rows + 1) * 4 + rows * vb + cols * vb
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks (NVML, sampled in-process during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.ok:
+            self._stop.set()
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvml unavailable"}
+        reasons = sorted(r for r in self.reasons if r != "gpu_idle")
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_sm),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline (oracle/_ref = the reference's own OmpMergeCsrmv; else the C port)
+# --------------------------------------------------------------------------------------------------
+def cpu_time(ro, col, val, x, budget_s):
+    """Times the CPU merge CsrMV on this host in the reference's protocol.  Returns dict."""
+    import oracle
+
+    if oracle.Reference.available():
+        impl, kind = oracle.Reference(), "reference"
+        threads = min(impl.num_procs(), 256)  # cpu_spmv.cpp:302-303
+        timer = impl.time_omp_merge_csrmv
+    else:
+        impl, kind = oracle.Oracle(), "port"
+        threads = impl.num_procs()
+        timer = impl.time_merge_csrmv
+    nnz = int(ro[-1])
+    ms1, _ = timer(ro, col, val, x, threads, 1)  # includes 4 untimed calls (cpu_spmv.cpp:380-392)
+    iters = int(max(3, min(200, budget_s * 1000.0 / max(ms1, 1e-3))))
+    ms, _ = timer(ro, col, val, x, threads, iters)
+    return {"ms": ms, "gflops": 2.0 * nnz / ms / 1e6, "cores": threads, "kind": kind, "iters": iters, "nnz": nnz}
+
+
+def host_sample(kind, dt, p, ro, cols, values, max_nnz):
+    """The first rows of the workload holding at most max_nnz nonzeros, as host numpy arrays."""
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    nnz = int(ro[-1])
+    rows = ro.numel() - 1
+    if nnz > max_nnz:
+        rows = int(torch.searchsorted(ro.to(torch.int64), torch.tensor(max_nnz), right=True)) - 1
+        rows = max(rows, 1)
+    ro_s = ro[: rows + 1].clone()
+    k1 = int(ro_s[-1])
+    col, val = fill(kind, ro, cols, 0, k1, dt, values, dev, p)
+    return ro_s.numpy(), col.cpu().numpy(), val.cpu().numpy(), rows, k1
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU path, all host threads, same config and metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from merge_spmv_b200 import generators as gen
+
+    name, kind, dt, p, scaling = workload_spec(args.workload, 1)
+    ro, cols, _ = build_row_offsets(kind, p)
+    vb = 8 if dt == torch.float64 else 4
+    # bounded sample: cap the matrix so K+W steps finish within a few minutes on slow hosts
+    budget_nnz = int(os.environ.get("MSPMV_REF_MAX_NNZ", 1 << 26))
+    ro_s, col, val, rows, nnz = host_sample(kind, dt, p, ro, cols, args.values, budget_nnz)
+    x = gen.vector(cols, dt, "ones" if args.values == "ones" else "random").numpy()
+    import oracle
+
+    if oracle.Reference.available():
+        impl, kindname = oracle.Reference(), "reference"
+        threads = min(impl.num_procs(), 256)
+        step = lambda n: impl.time_omp_merge_csrmv(ro_s, col, val, x, threads, n)[0]
+    else:
+        impl, kindname = oracle.Oracle(), "port"
+        threads = impl.num_procs()
+        step = lambda n: impl.time_merge_csrmv(ro_s, col, val, x, threads, n)[0]
+    # the reference harness itself does 4 untimed calls before timing (cpu_spmv.cpp:380-392)
+    ms1 = step(1)
+    steps = args.steps
+    if ms1 * (steps + args.warmup) > 180e3:  # keep the whole run within a few minutes
+        steps = max(3, int(180e3 / ms1) - args.warmup)
+    if args.warmup > 4:
+        step(args.warmup - 4)
+    ms = step(steps)
+    gflops = 2.0 * nnz / ms / 1e6
+    sample = (f"first {rows} rows / {nnz} nnz of {name} ({'full workload' if nnz == int(ro[-1]) else 'bounded sample'}), "
+              f"{steps} timed calls of OmpMergeCsrmv, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64" if vb == 8 else "f32", "data": "synthetic",
+        "config": {"workload": name, "rows": rows, "cols": cols, "nnz": nnz, "values": args.values,
+                   "l2": "inputs larger than L2"},
+        "cpu_baseline": {"value": gflops, "unit": UNIT, "cores": threads, "kind": kindname, "sample": sample},
+        "e2e": {"value": gflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="default")
+    ap.add_argument("--values", default="random", choices=["ones", "random"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--engine", default=None, choices=[None, "stream", "tile", "auto"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    import merge_spmv_b200 as ms
+    from merge_spmv_b200 import generators as gen
+    from merge_spmv_b200 import sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.engine:
+        ms.lib().mspmv_set_engine(args.engine.encode())
+
+    name, kind, dt, p, scaling = workload_spec(args.workload, world)
+    vb = 8 if dt == torch.float64 else 4
+    ro, cols, alpha = build_row_offsets(kind, p)
+    rows, nnz = ro.numel() - 1, int(ro[-1])
+    ro_np = ro.numpy()
+    xmode = "ones" if args.values == "ones" else "random"
+    x = gen.vector(cols, dt, xmode, device=dev)
+
+    shard = sharded.make_shard(ro_np, cols, rank, world,
+                               lambda k0, k1: fill(kind, ro, cols, k0, k1, dt, args.values, dev, p), dev)
+    op = sharded.ShardedSpmv(shard)
+    L = ms.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up + correctness guard (exact identity on ones; finite on random) ----------------
+    for _ in range(args.warmup):
+        y = op(x)
+    torch.cuda.synchronize()
+    if args.values == "ones":
+        lens = torch.diff(torch.from_numpy(ro_np[shard.x0: shard.x1 + 1])).to(dt).to(dev)
+        assert torch.equal(y, lens), "warm-up result is not the row-length vector"
+    else:
+        assert bool(torch.isfinite(y).all())
+
+    # ---- timed region: exactly K steps, events on the launching stream, max over ranks ---------
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = L.mspmv_launch_count()
+    with sampler:
+        start.record()
+        for _ in range(args.steps):
+            op(x)
+        stop.record()
+        stop.synchronize()
+    launches = L.mspmv_launch_count() - launches0
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_per_step = elapsed_ms / args.steps
+    gflops = 2.0 * nnz / ms_per_step / 1e6
+
+    # ---- roofline of the dominant kernel (per rank: its shard's compulsory bytes / step time) --
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    shard_bytes = algorithmic_bytes(shard.local_rows, cols, shard.nnz, vb)
+    achieved = shard_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"{name}@{world}")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_stream_kernel",
+                "algorithmic_bytes_per_launch": shard_bytes,
+                "note": "duration = whole step (stream kernel + carry fix-up kernel), CUDA events"}
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region --------------
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = max(3, min(args.steps, 50))
+        if world == 1:
+            # session = upload A once (the driver's setup, gpu_spmv.cu:542-556), then per step:
+            # x host->device, CsrMV, y device->host, pipelined over three streams
+            ro_h, col_h, val_h = ro_np, shard.col.cpu().numpy(), shard.val.cpu().numpy()
+            t0 = time.perf_counter()
+            sess = ms.SpmvSession(ro_h, col_h, val_h, cols, device=local_rank)
+            setup_ms = (time.perf_counter() - t0) * 1e3
+            xs = torch.empty((n_e2e, cols), dtype=dt).pin_memory()
+            ys = torch.empty((n_e2e, rows), dtype=dt).pin_memory()
+            xs[:] = x.cpu()
+            sess.apply_many(3, xs, ys)  # warm
+            t0 = time.perf_counter()
+            sess.apply_many(n_e2e, xs, ys)
+            dt_s = time.perf_counter() - t0
+            assert torch.equal(ys[n_e2e - 1].to(dev), y)
+            t0 = time.perf_counter()
+            for i in range(5):
+                sess.apply(xs[i % n_e2e], ys[i % n_e2e])
+            single_ms = (time.perf_counter() - t0) * 1e3 / 5
+            sess.close()
+            e2e = {"value": 2.0 * nnz * n_e2e / dt_s / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": cols * vb, "d2h_bytes_per_step": rows * vb, "steps": n_e2e,
+                   "api": "mspmv_session_apply_many (pinned host x in, host y out, 3-stage pipeline)",
+                   "unpipelined_ms_per_step": single_ms, "matrix_upload_ms": setup_ms,
+                   "matrix_upload_bytes": int(nnz * (vb + 4) + (rows + 1) * 4)}
+        else:
+            xh = x.cpu().pin_memory()
+            yh = torch.empty(shard.owned_rows, dtype=dt).pin_memory()
+            xd = torch.empty_like(x)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                xd.copy_(xh, non_blocking=True)
+                yh.copy_(op(xd), non_blocking=True)
+            barrier()
+            dt_s = time.perf_counter() - t0
+            tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = {"value": 2.0 * nnz * n_e2e / float(tt.item()) / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": cols * vb, "d2h_bytes_per_step": shard.owned_rows * vb,
+                   "steps": n_e2e, "api": "ShardedSpmv with pinned host x / y per rank"}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        budget_nnz = int(os.environ.get("MSPMV_REF_MAX_NNZ", 1 << 26))
+        ro_s, col_s, val_s, rows_s, nnz_s = host_sample(kind, dt, p, ro, cols, args.values, budget_nnz)
+        c = cpu_time(ro_s, col_s, val_s, x.cpu().numpy(), budget_s=15.0)
+        cpu = {"value": c["gflops"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
+               "ms_per_step": c["ms"],
+               "sample": f"first {rows_s} rows / {nnz_s} nnz of {name} "
+                         f"({'full workload' if nnz_s == nnz else 'bounded sample'}), {c['iters']} timed calls"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64" if vb == 8 else "f32", "data": "synthetic",
+            "config": {"workload": name, "rows": rows, "cols": cols, "nnz": nnz, "values": args.values,
+                       "columns": "banded" if kind == "banded" else "stratified-uniform, sorted, distinct",
+                       "parallelism": f"merge-path shards x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
+                       "engine": args.engine or "stream"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "hbm_gbs_algorithmic": achieved * (1 if world == 1 else world),
+        }
+        if alpha is not None:
+            line["config"]["powerlaw_alpha"] = alpha
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,174 @@
+/*
+ * mergespmv.h -- C ABI of libmergespmv.so: Blackwell-native (sm_100a) merge-based CSR SpMV.
+ *
+ * This is the drop-in boundary for the one hot path of dumerrill/merge-spmv:
+ *
+ *     cub::DeviceSpmv::CsrMV<ValueT>(d_temp_storage, temp_storage_bytes, d_values,
+ *                                    d_row_offsets, d_column_indices, d_vector_x, d_vector_y,
+ *                                    num_rows, num_cols, num_nonzeros, stream, debug_synchronous)
+ *                                                    -- cub/device/device_spmv.cuh:129-164
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All citations are file:line in the
+ * reference tree.  Every function returns a cudaError_t value as int (0 == cudaSuccess), the
+ * reference's own error convention (dispatch_spmv_orig.cuh:563-749).
+ *
+ * There is NO CPU fallback anywhere behind this interface: without a CUDA device the compute
+ * entry points return the CUDA error they hit.
+ */
+#ifndef MERGESPMV_H
+#define MERGESPMV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSPMV_VERSION_MAJOR 0
+#define MSPMV_VERSION_MINOR 1
+
+/* cudaStream_t is passed as void* so that this header needs no CUDA headers. */
+typedef void* mspmv_stream_t;
+
+/* -------------------------------------------------------------------------------------------
+ * 1. y = A*x -- replaces cub::DeviceSpmv::CsrMV<float|double> (device_spmv.cuh:129-164) as
+ *    called by TestGpuMergeCsrmv (gpu_spmv.cu:390-395 size query, :404-409 warm-up, :424-429
+ *    timed loop).  Same argument order and meaning:
+ *      - d_temp_storage == NULL: write the required byte count to *temp_storage_bytes, launch
+ *        nothing, return 0 (dispatch_spmv_orig.cuh:651-655).
+ *      - otherwise *temp_storage_bytes must be >= that count, else cudaErrorInvalidValue
+ *        (util_device.cuh:90-93).  The blob needs no initialisation and is reusable.
+ *      - d_row_offsets has num_rows+1 zero-based entries, last == num_nonzeros.
+ *      - alpha = 1, beta = 0 (device_spmv.cuh:155-156): every y[r] is overwritten, empty rows
+ *        get 0.  Inputs are not modified.  Asynchronous on `stream` unless debug_synchronous.
+ *      - debug_synchronous != 0 logs each launch configuration to stdout and synchronises the
+ *        stream after every kernel (dispatch_spmv_orig.cuh:579,590,685,698,702,718,724,739).
+ *    Differences, all deliberate:
+ *      - never reads row_offsets[num_rows+1] and never adds a carry to y[num_rows]
+ *        (the reference's out-of-bounds read/write, App. A items 5-6);
+ *      - num_cols == 1 takes the general path and sums duplicates (the reference's
+ *        DeviceSpmv1ColKernel, dispatch_spmv_orig.cuh:68-93, keeps only the first nonzero);
+ *      - carry fix-up is deterministic for fp32 too (the reference uses atomics there,
+ *        agent_segment_fixup.cuh:226-260).
+ *    num_rows + num_nonzeros must be < 2^31 like the reference (dispatch_spmv_orig.cuh:608).
+ * ----------------------------------------------------------------------------------------- */
+int mspmv_csrmv_f32(void* d_temp_storage, size_t* temp_storage_bytes, const float* d_values,
+                    const int* d_row_offsets, const int* d_column_indices, const float* d_vector_x,
+                    float* d_vector_y, int num_rows, int num_cols, int num_nonzeros,
+                    mspmv_stream_t stream, int debug_synchronous);
+int mspmv_csrmv_f64(void* d_temp_storage, size_t* temp_storage_bytes, const double* d_values,
+                    const int* d_row_offsets, const int* d_column_indices, const double* d_vector_x,
+                    double* d_vector_y, int num_rows, int num_cols, int num_nonzeros,
+                    mspmv_stream_t stream, int debug_synchronous);
+
+/* y = alpha*A*x + beta*y -- the epilogue the reference's CLI (--alpha/--beta, gpu_spmv.cu:721-722)
+ * and SpmvGold (gpu_spmv.cu:72-92) accept but its merge kernels leave disabled
+ * (dispatch_spmv_orig.cuh:789-838; agent_spmv_orig.cuh:386-396).  beta == 0 never reads y. */
+int mspmv_csrmv_axpby_f32(void* d_temp_storage, size_t* temp_storage_bytes, const float* d_values,
+                          const int* d_row_offsets, const int* d_column_indices,
+                          const float* d_vector_x, float* d_vector_y, int num_rows, int num_cols,
+                          int num_nonzeros, float alpha, float beta, mspmv_stream_t stream,
+                          int debug_synchronous);
+int mspmv_csrmv_axpby_f64(void* d_temp_storage, size_t* temp_storage_bytes, const double* d_values,
+                          const int* d_row_offsets, const int* d_column_indices,
+                          const double* d_vector_x, double* d_vector_y, int num_rows, int num_cols,
+                          int num_nonzeros, double alpha, double beta, mspmv_stream_t stream,
+                          int debug_synchronous);
+
+/* -------------------------------------------------------------------------------------------
+ * 2. Merge-path coordinates (bit-exact against the reference's MergePathSearch,
+ *    cpu_spmv.cpp:223-245 == cub/thread/thread_search.cuh:53-84; what DeviceSpmvSearchKernel,
+ *    dispatch_spmv_orig.cuh:104-143, computes per tile).
+ * ----------------------------------------------------------------------------------------- */
+
+/* Device: for each of n diagonals (device array) write (x = row index, y = nonzero index) to
+ * d_coords[2*i], d_coords[2*i+1].  List A is row_end_offsets = d_row_offsets + 1. */
+int mspmv_merge_path_search(const int* d_row_offsets, int num_rows, int num_nonzeros,
+                            const int* d_diagonals, int n, int* d_coords, mspmv_stream_t stream);
+
+/* Device: the start coordinate of every threadblock's diagonal swath for this problem shape,
+ * exactly as mspmv_csrmv_* computes them in-kernel, plus the final end coordinate.
+ * Size query: d_coords == NULL writes the swath count to *num_swaths.  Otherwise writes
+ * 2*(*num_swaths+1) ints to d_coords (device memory). */
+int mspmv_csrmv_swath_coords(const int* d_row_offsets, int num_rows, int num_nonzeros,
+                             int value_bytes, int* num_swaths, int* d_coords,
+                             mspmv_stream_t stream);
+
+/* Host: same search on host memory (used to cut the matrix into per-GPU shards). */
+void mspmv_host_merge_path_search(const int* row_offsets, int num_rows, int num_nonzeros,
+                                  int64_t diagonal, int* out_x, int* out_y);
+
+/* -------------------------------------------------------------------------------------------
+ * 3. Multi-GPU sharding by the same merge decomposition (new surface: the reference is
+ *    single-GPU; README.md:5 and the paper's section III.A only assert that the
+ *    decomposition partitions hierarchically).  One process per GPU; shard g of p owns
+ *    diagonals [g*ceil((rows+nnz)/p), ...) exactly like thread g of OmpMergeCsrmv
+ *    (cpu_spmv.cpp:311-321).
+ * ----------------------------------------------------------------------------------------- */
+
+/* Host: cut points.  coords[2*g], coords[2*g+1] = (row, nonzero) where shard g starts,
+ * g = 0..num_shards (last entry = (num_rows, num_nonzeros)). */
+void mspmv_shard_partition(const int* row_offsets, int num_rows, int num_nonzeros, int num_shards,
+                           int* coords);
+
+/* Host: local CSR row offsets of one shard.  The shard holds rows [x0, x1) that END in it plus
+ * one trailing partial row (row x1, possibly empty): local_rows = x1 - x0 + 1 entries of y, the
+ * last of which is the carry-out (cpu_spmv.cpp:336-344).  Writes local_rows+1 offsets rebased
+ * by -y0 to local_row_offsets. */
+void mspmv_shard_row_offsets(const int* row_offsets, int x0, int y0, int x1, int y1,
+                             int* local_row_offsets);
+
+/* Device: after all shards' (row, carry) records have been all-gathered (one NCCL call; a
+ * record is the int32 row followed by the value), fold the carries of shards 0..p-2 into the
+ * local y slice in shard order, skipping rows >= num_rows_global -- the serial fix-up of
+ * cpu_spmv.cpp:348-352.  d_y_local[i] is global row y_row_begin + i, y_rows entries. */
+int mspmv_apply_carries_f32(float* d_y_local, int y_row_begin, int y_rows, int num_rows_global,
+                            const int* d_carry_rows, const float* d_carry_vals, int num_shards,
+                            mspmv_stream_t stream);
+int mspmv_apply_carries_f64(double* d_y_local, int y_row_begin, int y_rows, int num_rows_global,
+                            const int* d_carry_rows, const double* d_carry_vals, int num_shards,
+                            mspmv_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * 4. Host-buffer operator ("session"): the gpu_spmv driver's own protocol -- upload the CSR
+ *    once (gpu_spmv.cu:542-556), then apply it repeatedly (:421-432) -- behind one handle, so
+ *    that callers with host memory do not touch CUDA.  create() uploads A (setup); apply()
+ *    copies x host->device, runs mspmv_csrmv_*, copies y device->host, and returns when y is
+ *    valid.  value_bytes is 4 (float) or 8 (double).
+ * ----------------------------------------------------------------------------------------- */
+typedef struct mspmv_session mspmv_session;
+
+int mspmv_session_create(mspmv_session** out, int device, int value_bytes, int num_rows,
+                         int num_cols, int num_nonzeros, const int* row_offsets,
+                         const int* column_indices, const void* values);
+int mspmv_session_apply(mspmv_session* s, const void* x_host, void* y_host);
+/* Pipelined stream of n right-hand sides (xs: n*num_cols values, ys: n*num_rows values, both
+ * ideally pinned): copies, kernels and read-backs of consecutive vectors overlap. */
+int mspmv_session_apply_many(mspmv_session* s, int n, const void* xs_host, void* ys_host);
+void mspmv_session_destroy(mspmv_session* s);
+
+/* Pinned host memory helpers for the session's callers. */
+int mspmv_host_alloc(void** out, size_t bytes);
+int mspmv_host_free(void* p);
+
+/* -------------------------------------------------------------------------------------------
+ * 5. Introspection.
+ * ----------------------------------------------------------------------------------------- */
+int mspmv_version(void); /* major*100 + minor */
+/* Kernel launches issued by this library since load (all entry points). */
+uint64_t mspmv_launch_count(void);
+/* Launch geometry mspmv_csrmv_* uses for a shape: out[0] = swaths (threadblocks),
+ * out[1] = threads per block, out[2] = merge items per tile, out[3] = dynamic smem bytes,
+ * out[4] = kernels per call. */
+int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out);
+const char* mspmv_error_string(int err);
+/* Test hook: pick the kernel engine for subsequent calls in this process: "stream" (persistent
+ * TMA-fed swaths, the default), "tile" (one threadblock per tile + search kernel) or "auto".
+ * Also settable with the MSPMV_ENGINE environment variable.  Returns 0, or 1 for a bad name. */
+int mspmv_set_engine(const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MERGESPMV_H */

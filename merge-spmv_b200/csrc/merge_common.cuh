@@ -1,0 +1,191 @@
+// merge_common.cuh -- device building blocks shared by the sm_100a merge-based CsrMV kernels.
+//
+// Reference behaviour being re-implemented (file:line in /root/reference):
+//   MergePathSearch            cub/thread/thread_search.cuh:53-84 == cpu_spmv.cpp:223-245
+//   per-thread merge walk      cub/agent/agent_spmv_orig.cuh:557-578 (staged), :327-358 (direct)
+//   reduce-by-key scan op      cub/thread/thread_operators.cuh:278-302 (ReduceByKeyOp)
+//   block reduce-by-key        agent_spmv_orig.cuh:583-626 (BlockScan of KeyValuePair)
+// The block-wide scan of (row, partial) pairs is replaced by a warp-shuffle segmented scan of
+// (row-ended flag, tail partial) -- one element per thread instead of one per merge item.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mspmv {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// Merge-path search along one diagonal of (row_end_offsets  (+)  natural numbers).
+// `row_end(i)` returns list A element i (0 <= i < a_len); list B element j is b_base + j.
+// Returns the smallest x in [max(diag - b_len, 0), min(diag, a_len)] with
+// row_end(x) > b_base + diag - x - 1 (ties consume A first), and y = diag - x: the coordinate
+// is unique, so any search order gives the reference's result bit for bit.
+// ---------------------------------------------------------------------------------------------
+template <typename RowEndFn>
+__device__ __forceinline__ int2 merge_path_search(int diag, RowEndFn row_end, int a_len, int b_len,
+                                                  int b_base)
+{
+    int lo = max(diag - b_len, 0);
+    int hi = min(diag, a_len);
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (row_end(mid) <= b_base + diag - mid - 1)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return make_int2(min(lo, a_len), diag - lo);
+}
+
+// Search in global memory over the whole matrix (tile / swath / shard boundaries).
+__device__ __forceinline__ int2 merge_path_search_global(int64_t diag64, const int* __restrict__ row_end_offsets,
+                                                         int num_rows, int num_nonzeros)
+{
+    // diagonals past the end clamp to (num_rows, num_nonzeros)
+    int64_t total = (int64_t)num_rows + num_nonzeros;
+    int diag = (int)(diag64 < total ? diag64 : total);
+    return merge_path_search(
+        diag, [&](int i) { return __ldg(row_end_offsets + i); }, num_rows, num_nonzeros, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Segmented (reduce-by-key) scan element: `ended` = a row end occurred at or after the segment
+// start, `val` = partial sum since the last row end.  combine(a, b) with a earlier than b is
+// ReduceByKeyOp (thread_operators.cuh:290-300) specialised to "key changed" flags.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Seg {
+    T val;
+    int ended;
+};
+
+template <typename T>
+__device__ __forceinline__ Seg<T> seg_combine(const Seg<T>& a, const Seg<T>& b)
+{
+    Seg<T> r;
+    r.ended = a.ended | b.ended;
+    r.val = b.ended ? b.val : a.val + b.val;
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ T shfl_up(T v, int d)
+{
+    return __shfl_up_sync(kFull, v, d);
+}
+
+// Inclusive segmented scan across the 32 lanes of a warp.
+template <typename T>
+__device__ __forceinline__ Seg<T> warp_seg_scan_inclusive(Seg<T> s, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+        T v = shfl_up(s.val, d);
+        int e = __shfl_up_sync(kFull, s.ended, d);
+        if (lane >= d) {
+            if (!s.ended) s.val += v;
+            s.ended |= e;
+        }
+    }
+    return s;
+}
+
+// Block-wide exclusive segmented scan over NWARPS*32 threads (all must call).
+//   in        this thread's element
+//   carry_in  element logically preceding thread 0 (the previous tile's carry-out, or {0,0})
+//   excl      out: combine(carry_in, elements of threads 0..t-1)
+//   total     out: combine(carry_in, all elements) -- identical in every thread
+// s_warp must hold NWARPS Seg<T>.  Contains one named barrier among the participating threads.
+template <typename T, int NWARPS>
+__device__ __forceinline__ void block_seg_scan_exclusive(Seg<T> in, Seg<T> carry_in, Seg<T>* s_warp,
+                                                         int tid, int barrier_id, Seg<T>& excl,
+                                                         Seg<T>& total)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    Seg<T> inc = warp_seg_scan_inclusive(in, lane);
+    if (lane == 31) s_warp[warp] = inc;
+
+    Seg<T> prev;  // warp-exclusive
+    prev.val = shfl_up(inc.val, 1);
+    prev.ended = __shfl_up_sync(kFull, inc.ended, 1);
+    if (lane == 0) {
+        prev.val = T(0);
+        prev.ended = 0;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(NWARPS * 32) : "memory");
+
+    Seg<T> run = carry_in;
+    Seg<T> before = carry_in;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+        if (w == warp) before = run;
+        run = seg_combine(run, s_warp[w]);
+    }
+    excl = seg_combine(before, prev);
+    total = run;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-thread merge walk over IPT consecutive merge items of a tile.
+//   row_end(i)   absolute nonzero index at which local row i ends; row_end(nrows) must be a
+//                sentinel >= any nonzero index (INT_MAX) -- this replaces the reference's read
+//                of one element past the tile
+//   prod(j)      value*x[col] of local nonzero j (tile-relative)
+//   out(i, v)    store the finished sum of local row i
+// Produces this thread's scan element (ended, tail) and, for the first row that ends inside the
+// thread's span, (head_row, head_val), which still lacks the carry-in from earlier threads.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int IPT, typename RowEndFn, typename ProdFn, typename OutFn>
+__device__ __forceinline__ void thread_merge_walk(int diag, int items, int nrows, int nnzs, int y0,
+                                                  RowEndFn row_end, ProdFn prod, OutFn out,
+                                                  Seg<T>& elem, int& head_row, T& head_val)
+{
+    diag = min(diag, items);
+    int2 c = merge_path_search(diag, row_end, nrows, nnzs, y0);
+    int tx = c.x;        // local row
+    int ty = y0 + c.y;   // absolute nonzero index
+    int cur_end = row_end(tx);
+    T running = T(0);
+    elem.ended = 0;
+    head_row = 0;
+    head_val = T(0);
+
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        if (diag + i < items) {
+            if (ty < cur_end) {
+                running += prod(ty - y0);
+                ++ty;
+            } else {
+                if (!elem.ended) {
+                    elem.ended = 1;
+                    head_row = tx;
+                    head_val = running;
+                } else {
+                    out(tx, running);
+                }
+                running = T(0);
+                ++tx;
+                cur_end = row_end(tx);
+            }
+        }
+    }
+    elem.val = running;
+}
+
+// y = alpha*sum + beta*y_old epilogue (SpmvGold, gpu_spmv.cu:72-92); AXPBY=false is y = sum.
+template <typename T, bool AXPBY>
+__device__ __forceinline__ T epilogue(T sum, T alpha, T beta, const T* y_ptr)
+{
+    if (AXPBY) {
+        T r = alpha * sum;
+        if (beta != T(0)) r += beta * (*y_ptr);
+        return r;
+    }
+    return sum;
+}
+
+}  // namespace mspmv

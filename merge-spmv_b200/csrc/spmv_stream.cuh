@@ -1,0 +1,499 @@
+// spmv_stream.cuh -- "stream" engine: persistent, TMA-fed merge-based CsrMV for sm_100a.
+//
+// Decomposition (the reference's, applied recursively -- README.md:5, paper section III.A):
+//   GPU  -> G threadblocks: block c owns the contiguous diagonal swath [c*S, (c+1)*S) of the
+//           (row_end_offsets (+) N_nnz) merge path, S = ceil((rows+nnz)/G) -- exactly thread c
+//           of OmpMergeCsrmv with p = G (cpu_spmv.cpp:311-321).  G = CTAs resident on the GPU.
+//   block -> tiles of TILE = 256*IPT merge items walked in order; the partial row that crosses a
+//           tile boundary is carried in registers, so only ONE carry per block reaches global
+//           memory (the reference emits one per tile, agent_spmv_orig.cuh:906-913).
+//   tile -> 256 threads x IPT items: per-thread MergePathSearch in shared memory
+//           (agent_spmv_orig.cuh:539-545), serial walk (:557-578), warp-shuffle segmented scan.
+//
+// Data movement: a dedicated producer warp streams the swath's values / column indices and its
+// row offsets into two shared-memory rings with cp.async.bulk (TMA, SASS UBLKCP) completing on
+// mbarriers; ring slots are fixed-size chunks of the *absolute* index space, so every bulk copy
+// is 16-byte aligned no matter where the swath starts (ragged ends of the first/last chunk, and
+// arrays whose base is not 16-byte aligned, are patched with a handful of scalar copies by the
+// same warp).  Consumers never wait on HBM for the stream, only on L2 for the x gathers.
+#pragma once
+
+#include <limits.h>
+
+#include "merge_common.cuh"
+
+namespace mspmv {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (mbarrier + bulk async copy)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Geometry
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct StreamCfg {
+    static constexpr int CONSUMERS = 256;                      // 8 consumer warps
+    static constexpr int THREADS = CONSUMERS + 32;             // + 1 producer warp
+    static constexpr int IPT = sizeof(T) == 8 ? 7 : 9;         // odd: conflict-free strided smem walk
+    static constexpr int TILE = CONSUMERS * IPT;
+    static constexpr int CH = sizeof(T) == 8 ? 512 : 1024;     // nonzeros per ring chunk
+    static constexpr int NSLOT = 8;                            // chunks in the nonzero ring
+    static constexpr int RN = CH * NSLOT;                      // ring capacity (power of two)
+    static constexpr int RCH = 512;                            // row offsets per ring chunk
+    static constexpr int RSLOT = 8;
+    static constexpr int RR = RCH * RSLOT;
+    static constexpr int CTAS_PER_SM = 2;
+    static constexpr int MIN_SWATH = 1024;                     // merge items; small inputs use fewer blocks
+    static_assert((RN & (RN - 1)) == 0 && (RR & (RR - 1)) == 0, "rings are power-of-two sized");
+    static_assert(RN >= TILE + 2 * CH && RR >= TILE + 1 + 2 * RCH, "ring must hold one tile plus slack");
+};
+
+template <typename T>
+struct StreamSmem {
+    using C = StreamCfg<T>;
+    alignas(128) T val[C::RN];        // values, overwritten in place by value*x[col]
+    alignas(128) int col[C::RN];
+    alignas(128) int row[C::RR];      // row_offsets entries (index j = row + 1)
+    alignas(16) T y[C::TILE];         // finished row sums of the current tile
+    Seg<T> warp[C::CONSUMERS / 32];
+    alignas(8) uint64_t full_n[C::NSLOT];
+    uint64_t empty_n[C::NSLOT];
+    uint64_t full_r[C::RSLOT];
+    uint64_t empty_r[C::RSLOT];
+    int2 swath[2];                    // start / end coordinate of this block's swath
+    int2 tile_end;
+};
+
+struct StreamGeom {
+    int num_swaths = 0;
+    int swath_items = 0;
+    int threads = 0;
+    int tile_items = 0;
+    size_t smem_bytes = 0;
+};
+
+template <typename T>
+static StreamGeom stream_geometry(int64_t merge_items, int sm_count)
+{
+    using C = StreamCfg<T>;
+    StreamGeom g;
+    int64_t want = (merge_items + C::MIN_SWATH - 1) / C::MIN_SWATH;
+    int64_t cap = (int64_t)sm_count * C::CTAS_PER_SM;
+    int64_t n = want < 1 ? 1 : (want > cap ? cap : want);
+    g.num_swaths = (int)n;
+    g.swath_items = (int)((merge_items + n - 1) / n);
+    g.threads = C::THREADS;
+    g.tile_items = C::TILE;
+    g.smem_bytes = sizeof(StreamSmem<T>) + 128;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative 32-ary merge-path search in global memory: ~log33(range) dependent loads
+// instead of log2(range).  Same unique answer as merge_path_search().
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int2 warp_merge_path_search_global(int64_t diag64,
+                                                              const int* __restrict__ row_end_offsets,
+                                                              int num_rows, int num_nonzeros, int lane)
+{
+    int64_t total = (int64_t)num_rows + num_nonzeros;
+    int diag = (int)(diag64 < total ? diag64 : total);
+    int lo = max(diag - num_nonzeros, 0);
+    int hi = min(diag, num_rows);
+    while (lo < hi) {
+        int span = hi - lo;
+        // 32 pivots strictly inside [lo, hi); duplicates are fine for tiny spans
+        int pivot = lo + (int)(((int64_t)span * (lane + 1)) / 33);
+        pivot = min(pivot, hi - 1);
+        bool go_up = __ldg(row_end_offsets + pivot) <= diag - pivot - 1;  // predicate is monotone in pivot
+        unsigned up = __ballot_sync(kFull, go_up);
+        int n_up = __popc(up);
+        int new_lo = n_up > 0 ? __shfl_sync(kFull, pivot, n_up - 1) + 1 : lo;
+        int new_hi = n_up < 32 ? __shfl_sync(kFull, pivot, n_up) : hi;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    return make_int2(min(lo, num_rows), diag - lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Producer helper: stage elements [lo, hi) of a global array into a ring.
+// Ring position of element i is (i + shift) & mask where shift = element misalignment of the
+// array base w.r.t. 16 bytes, so 16-byte-aligned global addresses land on 16-byte-aligned ring
+// positions.  The aligned middle goes by one bulk copy (lane 0); the < 16-byte ragged ends are
+// copied by lanes 1..; returns the bulk byte count (valid in lane 0).  The range never wraps the
+// ring except through the ragged tail, which is masked per element.
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__device__ __forceinline__ uint32_t stage_range(const E* __restrict__ base, int shift, int lo, int hi,
+                                                E* ring, int mask, uint64_t* bar, uint64_t policy,
+                                                int lane)
+{
+    constexpr int GRAN = 16 / (int)sizeof(E);
+    if (lo >= hi) return 0;
+    int lo_al = lo + ((GRAN - ((lo + shift) & (GRAN - 1))) & (GRAN - 1));  // first aligned index >= lo
+    int hi_al = hi - ((hi + shift) & (GRAN - 1));                          // last aligned index <= hi
+    uint32_t bytes = 0;
+    if (lo_al < hi_al) {
+        bytes = (uint32_t)(hi_al - lo_al) * (uint32_t)sizeof(E);
+    } else {
+        lo_al = hi;  // no aligned middle: everything is ragged head
+        hi_al = hi;
+    }
+    // ragged head [lo, lo_al) and tail [hi_al, hi): at most GRAN-1 elements each
+    int nhead = lo_al - lo, ntail = hi - hi_al;
+    if (lane < nhead) {
+        int i = lo + lane;
+        ring[(i + shift) & mask] = base[i];
+    } else if (lane >= 8 && lane - 8 < ntail) {
+        int i = hi_al + (lane - 8);
+        ring[(i + shift) & mask] = base[i];
+    }
+    if (lane == 0 && bytes) bulk_g2s(ring + ((lo_al + shift) & mask), base + lo_al, bytes, bar, policy);
+    return bytes;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool AXPBY>
+__global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) void spmv_stream_kernel(
+    const T* __restrict__ values, const int* __restrict__ row_offsets,
+    const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y, int num_rows,
+    int num_nonzeros, int swath_items, int2* __restrict__ swath_coords, int* __restrict__ carry_rows,
+    T* __restrict__ carry_vals, T alpha, T beta, int shift_v, int shift_c, int shift_r)
+{
+    using C = StreamCfg<T>;
+    constexpr int NCW = C::CONSUMERS / 32;
+    extern __shared__ unsigned char smem_raw[];
+    StreamSmem<T>& sm =
+        *reinterpret_cast<StreamSmem<T>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int64_t total_items = (int64_t)num_rows + num_nonzeros;
+    const int64_t d_begin64 = (int64_t)blockIdx.x * swath_items;
+    const int d_begin = (int)(d_begin64 < total_items ? d_begin64 : total_items);
+    const int64_t d_end64 = d_begin64 + swath_items;
+    const int d_end = (int)(d_end64 < total_items ? d_end64 : total_items);
+    const int* __restrict__ row_end_offsets = row_offsets + 1;
+
+    // ---- prologue: barriers + the two swath boundary searches (warps 0 and 1) -----------------
+    if (tid == C::CONSUMERS) {
+        for (int i = 0; i < C::NSLOT; ++i) {
+            mbar_init(&sm.full_n[i], 1);
+            mbar_init(&sm.empty_n[i], 1);
+        }
+        for (int i = 0; i < C::RSLOT; ++i) {
+            mbar_init(&sm.full_r[i], 1);
+            mbar_init(&sm.empty_r[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp < 2) {
+        int2 c = warp_merge_path_search_global(warp == 0 ? d_begin : d_end, row_end_offsets, num_rows,
+                                               num_nonzeros, lane);
+        if (lane == 0) sm.swath[warp] = c;
+    }
+    __syncthreads();
+    const int X0 = sm.swath[0].x, Y0 = sm.swath[0].y;
+    const int X1 = sm.swath[1].x, Y1 = sm.swath[1].y;
+    if (tid == 0) {
+        swath_coords[blockIdx.x] = sm.swath[0];
+        if (blockIdx.x == gridDim.x - 1) swath_coords[gridDim.x] = sm.swath[1];
+    }
+
+    // Chunk index ranges.  Nonzeros: absolute index i lives in chunk i / CH.  Row offsets are
+    // addressed by j = row + 1 (row_end_offsets[row] == row_offsets[j]); the swath needs
+    // j in [X0 + 1, X1 + 1).
+    const int kn_lo = Y0 / C::CH;
+    const int kn_hi = Y1 > Y0 ? (Y1 - 1) / C::CH + 1 : kn_lo;
+    const int J0 = X0 + 1, J1 = X1 + 1;
+    const int kr_lo = J0 / C::RCH;
+    const int kr_hi = J1 > J0 ? (J1 - 1) / C::RCH + 1 : kr_lo;
+
+    if (warp == NCW) {
+        // =================================== producer warp =====================================
+        const uint64_t policy = l2_policy_evict_first();
+        int kn = kn_lo, kr = kr_lo;
+        while (kn < kn_hi || kr < kr_hi) {
+            bool progress = false;
+            if (kn < kn_hi) {
+                int kk = kn - kn_lo, slot = kk % C::NSLOT, use = kk / C::NSLOT;
+                bool free_slot = true;
+                if (use > 0) {
+                    if (lane == 0) free_slot = mbar_test_wait(&sm.empty_n[slot], (use - 1) & 1);
+                    free_slot = __shfl_sync(kFull, free_slot, 0);
+                }
+                if (free_slot) {
+                    int lo = max(kn * C::CH, Y0), hi = (int)min((int64_t)(kn + 1) * C::CH, (int64_t)Y1);
+                    uint32_t b = stage_range<T>(values, shift_v, lo, hi, sm.val, C::RN - 1,
+                                                &sm.full_n[slot], policy, lane);
+                    b += stage_range<int>(column_indices, shift_c, lo, hi, sm.col, C::RN - 1,
+                                          &sm.full_n[slot], policy, lane);
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (b) mbar_arrive_expect_tx(&sm.full_n[slot], b);
+                        else mbar_arrive(&sm.full_n[slot]);
+                    }
+                    ++kn;
+                    progress = true;
+                }
+            }
+            if (kr < kr_hi) {
+                int kk = kr - kr_lo, slot = kk % C::RSLOT, use = kk / C::RSLOT;
+                bool free_slot = true;
+                if (use > 0) {
+                    if (lane == 0) free_slot = mbar_test_wait(&sm.empty_r[slot], (use - 1) & 1);
+                    free_slot = __shfl_sync(kFull, free_slot, 0);
+                }
+                if (free_slot) {
+                    int lo = max(kr * C::RCH, J0), hi = (int)min((int64_t)(kr + 1) * C::RCH, (int64_t)J1);
+                    uint32_t b = stage_range<int>(row_offsets, shift_r, lo, hi, sm.row, C::RR - 1,
+                                                  &sm.full_r[slot], policy, lane);
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (b) mbar_arrive_expect_tx(&sm.full_r[slot], b);
+                        else mbar_arrive(&sm.full_r[slot]);
+                    }
+                    ++kr;
+                    progress = true;
+                }
+            }
+            if (!progress) __nanosleep(64);
+        }
+        return;
+    }
+
+    // ===================================== consumer warps ======================================
+    int tx0 = X0, ty0 = Y0;          // current tile start coordinate
+    int d = d_begin;                 // current diagonal
+    int prod_upto = Y0;              // products exist for nonzeros [.., prod_upto)
+    int n_waited = 0, r_waited = 0;  // chunks (relative index) already acquired
+    int n_released = 0, r_released = 0;
+    Seg<T> carry;                    // partial row carried across tiles, in registers
+    carry.val = T(0);
+    carry.ended = 0;
+
+    while (d < d_end) {
+        const int items = min(C::TILE, d_end - d);
+        const int y_need = min(ty0 + items, Y1);          // exclusive bound on nonzeros touched
+        const int nrows_max = min(items, X1 - tx0);       // row ends this tile can contain
+
+        // ---- acquire the chunks this tile can touch -------------------------------------------
+        if (y_need > Y0) {
+            int kk_need = (y_need - 1) / C::CH - kn_lo;
+            while (n_waited <= kk_need) {
+                mbar_wait(&sm.full_n[n_waited % C::NSLOT], (n_waited / C::NSLOT) & 1);
+                ++n_waited;
+            }
+        }
+        if (nrows_max > 0) {
+            int kk_need = (tx0 + nrows_max) / C::RCH - kr_lo;  // j = tx0 + nrows_max is the last needed
+            while (r_waited <= kk_need) {
+                mbar_wait(&sm.full_r[r_waited % C::RSLOT], (r_waited / C::RSLOT) & 1);
+                ++r_waited;
+            }
+        }
+
+        // ---- phase A: products value * x[col] for the not-yet-multiplied nonzeros ---------------
+        // (strip-mined gather, agent_spmv_orig.cuh:472-494; in place in the value ring)
+        {
+            int cidx[C::IPT];
+            T xv[C::IPT];
+#pragma unroll
+            for (int i = 0; i < C::IPT; ++i) {
+                int j = prod_upto + tid + i * C::CONSUMERS;
+                cidx[i] = j < y_need ? sm.col[(j + shift_c) & (C::RN - 1)] : -1;
+            }
+#pragma unroll
+            for (int i = 0; i < C::IPT; ++i) xv[i] = cidx[i] >= 0 ? __ldg(x + cidx[i]) : T(0);
+#pragma unroll
+            for (int i = 0; i < C::IPT; ++i) {
+                int j = prod_upto + tid + i * C::CONSUMERS;
+                if (j < y_need) {
+                    int p = (j + shift_v) & (C::RN - 1);
+                    sm.val[p] = sm.val[p] * xv[i];
+                }
+            }
+            prod_upto = max(prod_upto, y_need);
+        }
+        fence_proxy_async();  // ring slots written here are later overwritten by bulk copies
+        named_bar_sync(1, C::CONSUMERS);
+
+        // ---- phase B: per-thread merge walk + segmented scan -------------------------------------
+        auto row_end = [&](int i) {
+            return i < nrows_max ? sm.row[(tx0 + i + 1 + shift_r) & (C::RR - 1)] : INT_MAX;
+        };
+        auto prod = [&](int j) { return sm.val[(ty0 + j + shift_v) & (C::RN - 1)]; };
+        const int nnz_max = y_need - ty0;
+        Seg<T> elem;
+        int head_row;
+        T head_val;
+        {
+            // thread_merge_walk, plus capture of the coordinate where the tile ends
+            int diag = min(tid * C::IPT, items);
+            int2 c = merge_path_search(diag, row_end, nrows_max, nnz_max, ty0);
+            int rx = c.x, ny = ty0 + c.y;
+            int cur_end = row_end(rx);
+            T running = T(0);
+            elem.ended = 0;
+            head_row = 0;
+            head_val = T(0);
+#pragma unroll
+            for (int i = 0; i < C::IPT; ++i) {
+                if (diag + i < items) {
+                    if (ny < cur_end) {
+                        running += prod(ny - ty0);
+                        ++ny;
+                    } else {
+                        if (!elem.ended) {
+                            elem.ended = 1;
+                            head_row = rx;
+                            head_val = running;
+                        } else {
+                            sm.y[rx] = running;
+                        }
+                        running = T(0);
+                        ++rx;
+                        cur_end = row_end(rx);
+                    }
+                }
+            }
+            elem.val = running;
+            if (diag < items && diag + C::IPT >= items) sm.tile_end = make_int2(tx0 + rx, ny);
+        }
+        Seg<T> excl, total;
+        block_seg_scan_exclusive<T, NCW>(elem, carry, sm.warp, tid, 1, excl, total);
+        if (elem.ended) sm.y[head_row] = head_val + excl.val;
+        named_bar_sync(1, C::CONSUMERS);
+
+        // ---- tile epilogue: coalesced y store, advance, release dead ring chunks ---------------
+        const int2 te = sm.tile_end;
+        const int nrows = te.x - tx0;
+        for (int r = tid; r < nrows; r += C::CONSUMERS)
+            y[tx0 + r] = epilogue<T, AXPBY>(sm.y[r], alpha, beta, y + tx0 + r);
+
+        if (tid == 0) {
+            while (n_released < n_waited && (int64_t)(kn_lo + n_released + 1) * C::CH <= te.y) {
+                mbar_arrive(&sm.empty_n[n_released % C::NSLOT]);
+                ++n_released;
+            }
+            // row chunk k holds j in [k*RCH, (k+1)*RCH); rows < te.x are dead, i.e. j <= te.x
+            while (r_released < r_waited && (int64_t)(kr_lo + r_released + 1) * C::RCH <= te.x + 1) {
+                mbar_arrive(&sm.empty_r[r_released % C::RSLOT]);
+                ++r_released;
+            }
+        }
+        carry.val = total.val;
+        carry.ended = 0;
+        tx0 = te.x;
+        ty0 = te.y;
+        d += items;
+    }
+
+    // swath carry-out (cpu_spmv.cpp:343-344): the row that continues into the next swath
+    if (tid == 0) {
+        carry_rows[blockIdx.x] = X1;
+        carry_vals[blockIdx.x] = carry.val;
+    }
+}
+
+template <typename T, bool AXPBY>
+static int stream_launch(const StreamGeom& g, const T* values, const int* row_offsets, const int* col,
+                         const T* x, T* y, int num_rows, int num_nonzeros, int2* swath_coords,
+                         int* carry_rows, T* carry_vals, T alpha, T beta, cudaStream_t stream)
+{
+    auto kernel = spmv_stream_kernel<T, AXPBY>;
+    static bool configured[64] = {};  // per template instantiation and device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (!configured[dev & 63]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        configured[dev & 63] = true;
+    }
+    int shift_v = (int)((reinterpret_cast<uintptr_t>(values) & 15) / sizeof(T));
+    int shift_c = (int)((reinterpret_cast<uintptr_t>(col) & 15) / sizeof(int));
+    int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
+    kernel<<<g.num_swaths, g.threads, g.smem_bytes, stream>>>(values, row_offsets, col, x, y, num_rows,
+                                                              num_nonzeros, g.swath_items, swath_coords,
+                                                              carry_rows, carry_vals, alpha, beta,
+                                                              shift_v, shift_c, shift_r);
+    return 0;
+}
+
+}  // namespace mspmv

@@ -1,0 +1,136 @@
+"""One-process-per-GPU sharding of a single CsrMV by the merge decomposition.
+
+New surface (the reference is single-GPU; README.md:5 and the paper's section III.A only state
+that the decomposition partitions hierarchically).  The cut is the one ``OmpMergeCsrmv`` makes
+between CPU threads (cpu_spmv.cpp:311-321) with p = world size:
+
+* rank g owns diagonals ``[g*ceil((rows+nnz)/p), ...)`` of the merge path, i.e. nonzeros
+  ``[y_g, y_{g+1})`` and the rows ``[x_g, x_{g+1})`` that END inside its span;
+* its shard is an ordinary local CSR with ``x_{g+1} - x_g + 1`` rows -- the last local row is the
+  (possibly empty) leading part of global row ``x_{g+1}`` -- so the same ``mspmv_csrmv_*`` kernel
+  runs unchanged and ``y_local[-1]`` is the carry-out (cpu_spmv.cpp:336-344);
+* carry *rows* are known to every rank from the partition, so only the p carry *values* are
+  exchanged: ONE ``all_gather`` (NCCL over NVLink) straight out of ``y_local[-1:]``;
+* ``mspmv_apply_carries_*`` then folds carries 0..p-2 into the owning rank's slice in shard order
+  with the ``row < num_rows`` guard -- the serial fix-up of cpu_spmv.cpp:348-352.
+
+``x`` is replicated, ``y`` stays sharded (rank g holds global rows ``[x_g, x_{g+1})``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .csrmv import _ptr, _stream, csrmv
+
+
+def partition(row_offsets_host: np.ndarray, world: int) -> np.ndarray:
+    """(world+1, 2) int32 cut coordinates (row, nonzero); host-side MergePathSearch."""
+    ro = np.ascontiguousarray(row_offsets_host, dtype=np.int32)
+    rows, nnz = ro.size - 1, int(ro[-1])
+    coords = np.zeros((world + 1, 2), dtype=np.int32)
+    _lib.lib().mspmv_shard_partition(ro.ctypes.data_as(C.c_void_p), rows, nnz, world,
+                                     coords.ctypes.data_as(C.c_void_p))
+    return coords
+
+
+def local_row_offsets(row_offsets_host: np.ndarray, coords: np.ndarray, rank: int) -> np.ndarray:
+    ro = np.ascontiguousarray(row_offsets_host, dtype=np.int32)
+    (x0, y0), (x1, y1) = coords[rank], coords[rank + 1]
+    out = np.zeros(int(x1 - x0) + 2, dtype=np.int32)
+    _lib.lib().mspmv_shard_row_offsets(ro.ctypes.data_as(C.c_void_p), int(x0), int(y0), int(x1), int(y1),
+                                       out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+@dataclass
+class Shard:
+    rank: int
+    world: int
+    coords: np.ndarray          # (world+1, 2)
+    rows_global: int
+    cols: int
+    row_offsets: torch.Tensor   # int32 [local_rows + 1], rebased to this shard's first nonzero
+    col: torch.Tensor           # int32 [y1 - y0]
+    val: torch.Tensor           # [y1 - y0]
+    carry_rows: torch.Tensor    # int32 [world]: global row each rank's carry belongs to
+
+    @property
+    def x0(self):
+        return int(self.coords[self.rank, 0])
+
+    @property
+    def x1(self):
+        return int(self.coords[self.rank + 1, 0])
+
+    @property
+    def y0(self):
+        return int(self.coords[self.rank, 1])
+
+    @property
+    def y1(self):
+        return int(self.coords[self.rank + 1, 1])
+
+    @property
+    def owned_rows(self):
+        return self.x1 - self.x0
+
+    @property
+    def local_rows(self):
+        return self.owned_rows + 1
+
+    @property
+    def nnz(self):
+        return self.y1 - self.y0
+
+
+def make_shard(row_offsets_host, cols, rank, world, fill, device) -> Shard:
+    """Build rank's shard.  ``fill(k0, k1)`` returns (col int32, val) tensors on ``device`` for the
+    global nonzero range [k0, k1) -- a slice of resident arrays or a generator."""
+    ro = np.ascontiguousarray(row_offsets_host, dtype=np.int32)
+    coords = partition(ro, world)
+    lro = local_row_offsets(ro, coords, rank)
+    y0, y1 = int(coords[rank, 1]), int(coords[rank + 1, 1])
+    col, val = fill(y0, y1)
+    return Shard(rank=rank, world=world, coords=coords, rows_global=ro.size - 1, cols=int(cols),
+                 row_offsets=torch.from_numpy(lro).to(device), col=col.contiguous(), val=val.contiguous(),
+                 carry_rows=torch.from_numpy(np.ascontiguousarray(coords[1:, 0])).to(device))
+
+
+def apply_carries(y_local, shard: Shard, carry_vals, stream=None):
+    """Device fold of the gathered carries into this rank's owned rows (cpu_spmv.cpp:348-352)."""
+    sfx = "f64" if y_local.dtype == torch.float64 else "f32"
+    fn = getattr(_lib.lib(), f"mspmv_apply_carries_{sfx}")
+    with torch.cuda.device(y_local.device):
+        _lib.check(fn(_ptr(y_local), shard.x0, shard.owned_rows, shard.rows_global,
+                      _ptr(shard.carry_rows), _ptr(carry_vals), shard.world, _stream(stream)),
+                   "apply_carries")
+
+
+class ShardedSpmv:
+    """y_shard = (A x)[x_g : x_{g+1}) on this rank; call collectively on all ranks."""
+
+    def __init__(self, shard: Shard, group=None, local_spmv=None, fold=None):
+        self.shard = shard
+        self.group = group
+        dev = shard.val.device
+        self.y_local = torch.zeros(shard.local_rows, dtype=shard.val.dtype, device=dev)
+        self.carries = torch.zeros(shard.world, dtype=shard.val.dtype, device=dev)
+        # injectable for the CPU (gloo) tests of the exchange logic; the defaults are the CUDA path
+        self._local_spmv = local_spmv or (lambda s, x, y: csrmv(s.row_offsets, s.col, s.val, x, y,
+                                                               num_cols=s.cols))
+        self._fold = fold or apply_carries
+
+    def __call__(self, x):
+        s = self.shard
+        self._local_spmv(s, x, self.y_local)
+        if s.world > 1:
+            # the single exchange step: p carry values, taken in place from the last local row
+            dist.all_gather_into_tensor(self.carries, self.y_local[s.local_rows - 1:], group=self.group)
+            self._fold(self.y_local, s, self.carries)
+        return self.y_local[:s.owned_rows]

@@ -1,0 +1,83 @@
+"""The C-ABI library loads and exports every symbol include/mergespmv.h declares; host-only
+entry points agree with the oracle.  CPU only -- no compute call is made without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_csr
+
+import merge_spmv_b200 as ms
+from merge_spmv_b200 import _lib, sharded
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mergespmv.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mspmv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    L = C.CDLL(ms.lib_path())
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/mergespmv.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(syms)
+
+
+def test_version_and_error_string():
+    L = ms.lib()
+    assert L.mspmv_version() == 1
+    assert b"invalid argument" in L.mspmv_error_string(1)
+    assert L.mspmv_set_engine(b"bogus") == 1
+    assert L.mspmv_set_engine(b"auto") == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    ro = torch.tensor([0, 1], dtype=torch.int32)
+    with pytest.raises(ms.MergeSpmvError):
+        ms.csrmv(ro, torch.zeros(1, dtype=torch.int32), torch.ones(1), torch.ones(1))
+
+
+def test_host_merge_path_search_matches_oracle(orc):
+    rng = np.random.default_rng(17)
+    L = ms.lib()
+    for _ in range(30):
+        rows = int(rng.integers(1, 300))
+        ro, _ = random_csr(rng, rows, 64, rng.uniform(0.1, 9), rng.uniform(0, 0.5), 1)
+        nnz = int(ro[-1])
+        for d in rng.integers(0, rows + nnz + 30, 50):
+            x, y = C.c_int(), C.c_int()
+            L.mspmv_host_merge_path_search(ro.ctypes.data_as(C.c_void_p), rows, nnz, int(d), C.byref(x), C.byref(y))
+            assert (x.value, y.value) == orc.merge_path_search(int(d), ro)
+
+
+def test_shard_partition_equals_cpu_thread_coords(orc):
+    # shard g of p == thread g of OmpMergeCsrmv with p threads (cpu_spmv.cpp:311-321)
+    rng = np.random.default_rng(23)
+    for _ in range(20):
+        rows = int(rng.integers(1, 500))
+        ro, _ = random_csr(rng, rows, 100, rng.uniform(0.1, 20), rng.uniform(0, 0.5), 2)
+        for p in (1, 2, 3, 4, 8, 16):
+            assert np.array_equal(sharded.partition(ro, p), orc.thread_coords(p, ro))
+
+
+def test_shard_row_offsets_cover_matrix():
+    rng = np.random.default_rng(29)
+    rows = 257
+    ro, _ = random_csr(rng, rows, 90, 6, 0.2, 2)
+    for p in (1, 2, 5, 8):
+        coords = sharded.partition(ro, p)
+        total = 0
+        for g in range(p):
+            lro = sharded.local_row_offsets(ro, coords, g)
+            (x0, y0), (x1, y1) = coords[g], coords[g + 1]
+            assert lro[0] == 0 and lro[-1] == y1 - y0 and np.all(np.diff(lro) >= 0)
+            assert lro.size == x1 - x0 + 2
+            total += lro[-1]
+        assert total == ro[-1]
