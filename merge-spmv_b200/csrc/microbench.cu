@@ -191,7 +191,7 @@ static void gather_suite(const char* tname, int sms)
     CK(cudaMalloc(&idx, n * sizeof(int)));
     CK(cudaMalloc(&vals, n * sizeof(T)));
     CK(cudaMalloc(&out, 64));
-    const int tables[] = {1 << 20, 2000000, 1 << 23, 20000000};
+    const int tables[] = {1 << 12, 1 << 14, 1 << 20, 2000000, 1 << 23, 20000000};
     const char* modes[] = {"uniform", "stratified64", "banded7"};
     fill_vals<T><<<(unsigned)((n + 255) / 256), 256>>>(vals, n, 7);
     for (int table_n : tables) {
