@@ -7,8 +7,13 @@
 //   block -> tiles of TILE = 256*IPT merge items walked in order; the partial row that crosses a
 //           tile boundary is carried in registers, so only ONE carry per block reaches global
 //           memory (the reference emits one per tile, agent_spmv_orig.cuh:906-913).
-//   tile -> 256 threads x IPT items: per-thread MergePathSearch in shared memory
-//           (agent_spmv_orig.cuh:539-545), serial walk (:557-578), warp-shuffle segmented scan.
+//   tile -> 256 threads x IPT consecutive merge items each.  Instead of one MergePathSearch per
+//           thread (agent_spmv_orig.cuh:539-545) the tile's row ends are scattered once into a
+//           shared-memory bitmap (bit p set <=> merge item p is a row end, p = row_end[r] - y0 +
+//           r - x0); a thread's start coordinate is then a popcount prefix -- the same unique
+//           coordinate MergePathSearch returns -- and its serial walk (:557-578) is a branch-free
+//           unrolled loop driven by its IPT flag bits.  Partial rows are closed by a warp-shuffle
+//           segmented scan; finished rows are written to y straight from registers.
 //
 // Data movement: a dedicated producer warp streams the swath's values / column indices and its
 // row offsets into two shared-memory rings with cp.async.bulk (TMA, SASS UBLKCP) completing on
@@ -106,18 +111,20 @@ template <typename T>
 struct StreamCfg {
     static constexpr int CONSUMERS = 256;                      // 8 consumer warps
     static constexpr int THREADS = CONSUMERS + 32;             // + 1 producer warp
-    static constexpr int IPT = sizeof(T) == 8 ? 7 : 9;         // odd: conflict-free strided smem walk
+    static constexpr int IPT = 9;                              // odd: conflict-free strided smem walk
     static constexpr int TILE = CONSUMERS * IPT;
-    static constexpr int CH = sizeof(T) == 8 ? 512 : 1024;     // nonzeros per ring chunk
+    static constexpr int CH = 512;                             // nonzeros per ring chunk
     static constexpr int NSLOT = 8;                            // chunks in the nonzero ring
     static constexpr int RN = CH * NSLOT;                      // ring capacity (power of two)
     static constexpr int RCH = 512;                            // row offsets per ring chunk
     static constexpr int RSLOT = 8;
     static constexpr int RR = RCH * RSLOT;
-    static constexpr int CTAS_PER_SM = 2;
+    static constexpr int BW = TILE / 32 + 2;                   // words per row-end bitmap
+    static constexpr int CTAS_PER_SM = 3;
     static constexpr int MIN_SWATH = 1024;                     // merge items; small inputs use fewer blocks
     static_assert((RN & (RN - 1)) == 0 && (RR & (RR - 1)) == 0, "rings are power-of-two sized");
     static_assert(RN >= TILE + 2 * CH && RR >= TILE + 1 + 2 * RCH, "ring must hold one tile plus slack");
+    static_assert(TILE % 32 == 0 && BW <= 96 && (IPT & 1) == 1 && IPT < 32, "bitmap layout");
 };
 
 template <typename T>
@@ -126,14 +133,13 @@ struct StreamSmem {
     alignas(128) T val[C::RN];        // values, overwritten in place by value*x[col]
     alignas(128) int col[C::RN];
     alignas(128) int row[C::RR];      // row_offsets entries (index j = row + 1)
-    alignas(16) T y[C::TILE];         // finished row sums of the current tile
-    Seg<T> warp[C::CONSUMERS / 32];
+    alignas(16) uint32_t bits[2][C::BW];  // row-end flags per merge item, double-buffered
+    alignas(16) Seg<T> warp[C::CONSUMERS / 32];
     alignas(8) uint64_t full_n[C::NSLOT];
     uint64_t empty_n[C::NSLOT];
     uint64_t full_r[C::RSLOT];
     uint64_t empty_r[C::RSLOT];
     int2 swath[2];                    // start / end coordinate of this block's swath
-    int2 tile_end;
 };
 
 struct StreamGeom {
@@ -226,9 +232,50 @@ __device__ __forceinline__ uint32_t stage_range(const E* __restrict__ base, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// The kernel
+// Phase A helpers: products value * x[col] in place in the value ring
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool AXPBY>
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+    float4 v;
+    __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+    __device__ __forceinline__ void mul(float a, float b, float c, float d)
+    {
+        v.x *= a;
+        v.y *= b;
+        v.z *= c;
+        v.w *= d;
+    }
+};
+template <>
+struct Vec4<double> {
+    double2 lo, hi;
+    __device__ __forceinline__ void load(const double* p)
+    {
+        lo = *reinterpret_cast<const double2*>(p);
+        hi = *reinterpret_cast<const double2*>(p + 2);
+    }
+    __device__ __forceinline__ void store(double* p) const
+    {
+        *reinterpret_cast<double2*>(p) = lo;
+        *reinterpret_cast<double2*>(p + 2) = hi;
+    }
+    __device__ __forceinline__ void mul(double a, double b, double c, double d)
+    {
+        lo.x *= a;
+        lo.y *= b;
+        hi.x *= c;
+        hi.y *= d;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The kernel.  VEC: values/column_indices bases are 16-byte aligned, so phase A works on aligned
+// groups of four nonzeros with 128-bit shared-memory accesses.
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool AXPBY, bool VEC>
 __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) void spmv_stream_kernel(
     const T* __restrict__ values, const int* __restrict__ row_offsets,
     const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y, int num_rows,
@@ -237,6 +284,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
 {
     using C = StreamCfg<T>;
     constexpr int NCW = C::CONSUMERS / 32;
+    constexpr int IPT = C::IPT;
     extern __shared__ unsigned char smem_raw[];
     StreamSmem<T>& sm =
         *reinterpret_cast<StreamSmem<T>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -250,7 +298,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     const int d_end = (int)(d_end64 < total_items ? d_end64 : total_items);
     const int* __restrict__ row_end_offsets = row_offsets + 1;
 
-    // ---- prologue: barriers + the two swath boundary searches (warps 0 and 1) -----------------
+    // ---- prologue: barriers, bitmaps, the two swath boundary searches (warps 0 and 1) ----------
     if (tid == C::CONSUMERS) {
         for (int i = 0; i < C::NSLOT; ++i) {
             mbar_init(&sm.full_n[i], 1);
@@ -262,6 +310,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         }
         fence_mbar_init();
     }
+    for (int i = tid; i < 2 * C::BW; i += C::THREADS) (&sm.bits[0][0])[i] = 0u;
     if (warp < 2) {
         int2 c = warp_merge_path_search_global(warp == 0 ? d_begin : d_end, row_end_offsets, num_rows,
                                                num_nonzeros, lane);
@@ -338,21 +387,22 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     }
 
     // ===================================== consumer warps ======================================
-    int tx0 = X0, ty0 = Y0;          // current tile start coordinate
-    int d = d_begin;                 // current diagonal
-    int prod_upto = Y0;              // products exist for nonzeros [.., prod_upto)
-    int n_waited = 0, r_waited = 0;  // chunks (relative index) already acquired
+    int x0 = X0, y0 = Y0;                            // current tile start coordinate
+    int d = d_begin;                                 // current diagonal
+    int prod_upto = VEC ? (Y0 & ~3) : Y0;            // products exist for nonzeros [.., prod_upto)
+    int n_waited = 0, r_waited = 0;                  // chunks (relative index) already acquired
     int n_released = 0, r_released = 0;
-    Seg<T> carry;                    // partial row carried across tiles, in registers
+    int buf = 0;
+    Seg<T> carry;                                    // partial row carried across tiles, in registers
     carry.val = T(0);
     carry.ended = 0;
 
     while (d < d_end) {
         const int items = min(C::TILE, d_end - d);
-        const int y_need = min(ty0 + items, Y1);          // exclusive bound on nonzeros touched
-        const int nrows_max = min(items, X1 - tx0);       // row ends this tile can contain
+        const int y_need = min(y0 + items, Y1);      // exclusive bound on nonzeros this tile can touch
+        const int nrows_max = min(items, X1 - x0);   // row ends this tile can contain
 
-        // ---- acquire the chunks this tile can touch -------------------------------------------
+        // ---- acquire the ring chunks this tile can touch ---------------------------------------
         if (y_need > Y0) {
             int kk_need = (y_need - 1) / C::CH - kn_lo;
             while (n_waited <= kk_need) {
@@ -361,27 +411,81 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
             }
         }
         if (nrows_max > 0) {
-            int kk_need = (tx0 + nrows_max) / C::RCH - kr_lo;  // j = tx0 + nrows_max is the last needed
+            int kk_need = (x0 + nrows_max) / C::RCH - kr_lo;  // j = x0 + nrows_max is the last needed
             while (r_waited <= kk_need) {
                 mbar_wait(&sm.full_r[r_waited % C::RSLOT], (r_waited / C::RSLOT) & 1);
                 ++r_waited;
             }
         }
 
-        // ---- phase A: products value * x[col] for the not-yet-multiplied nonzeros ---------------
-        // (strip-mined gather, agent_spmv_orig.cuh:472-494; in place in the value ring)
-        {
-            int cidx[C::IPT];
-            T xv[C::IPT];
+        // ---- row-end flags: merge item p = row_end[r] - y0 + (r - x0) is the end of row r --------
+        uint32_t* bits_w = sm.bits[buf];
+        for (int r = tid; r < nrows_max; r += C::CONSUMERS) {
+            int e = sm.row[(x0 + r + 1 + shift_r) & (C::RR - 1)];
+            int pos = e - y0 + r;
+            if (pos >= items) break;                 // positions increase with r
+            atomicOr(&bits_w[pos >> 5], 1u << (pos & 31));
+        }
+
+        // ---- phase A: products for the not-yet-multiplied nonzeros (agent_spmv_orig.cuh:472-494) --
+        if (VEC) {
+            // aligned groups of four nonzeros; two groups per thread in flight, then the remainder
+            constexpr int GROUPS = (C::TILE / 4 + 1 + C::CONSUMERS - 1) / C::CONSUMERS;
+            const int pa_hi = (y_need + 3) & ~3;
+            auto load_cols = [&](int j) {
+                int4 c = *reinterpret_cast<const int4*>(&sm.col[j & (C::RN - 1)]);
+                if (j < Y0 || j + 4 > Y1) {          // swath edge: slots outside [Y0, Y1) hold no data
+                    if (j + 0 < Y0 || j + 0 >= Y1) c.x = 0;
+                    if (j + 1 < Y0 || j + 1 >= Y1) c.y = 0;
+                    if (j + 2 < Y0 || j + 2 >= Y1) c.z = 0;
+                    if (j + 3 < Y0 || j + 3 >= Y1) c.w = 0;
+                }
+                return c;
+            };
+            auto finish = [&](int j, T a, T b, T c, T dd) {
+                T* p = &sm.val[j & (C::RN - 1)];
+                Vec4<T> v;
+                v.load(p);
+                v.mul(a, b, c, dd);
+                v.store(p);
+            };
 #pragma unroll
-            for (int i = 0; i < C::IPT; ++i) {
+            for (int g0 = 0; g0 < GROUPS; g0 += 2) {
+                const int ja = prod_upto + 4 * (tid + g0 * C::CONSUMERS);
+                const int jb = ja + 4 * C::CONSUMERS;
+                const bool has_a = ja < pa_hi, has_b = (g0 + 1 < GROUPS) && jb < pa_hi;
+                int4 ca = make_int4(0, 0, 0, 0), cb = make_int4(0, 0, 0, 0);
+                if (has_a) ca = load_cols(ja);
+                if (has_b) cb = load_cols(jb);
+                T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0), b0 = T(0), b1 = T(0), b2 = T(0), b3 = T(0);
+                if (has_a) {
+                    a0 = __ldg(x + ca.x);
+                    a1 = __ldg(x + ca.y);
+                    a2 = __ldg(x + ca.z);
+                    a3 = __ldg(x + ca.w);
+                }
+                if (has_b) {
+                    b0 = __ldg(x + cb.x);
+                    b1 = __ldg(x + cb.y);
+                    b2 = __ldg(x + cb.z);
+                    b3 = __ldg(x + cb.w);
+                }
+                if (has_a) finish(ja, a0, a1, a2, a3);
+                if (has_b) finish(jb, b0, b1, b2, b3);
+            }
+            prod_upto = max(prod_upto, pa_hi);
+        } else {
+            int cidx[IPT];
+            T xv[IPT];
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
                 int j = prod_upto + tid + i * C::CONSUMERS;
                 cidx[i] = j < y_need ? sm.col[(j + shift_c) & (C::RN - 1)] : -1;
             }
 #pragma unroll
-            for (int i = 0; i < C::IPT; ++i) xv[i] = cidx[i] >= 0 ? __ldg(x + cidx[i]) : T(0);
+            for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? __ldg(x + cidx[i]) : T(0);
 #pragma unroll
-            for (int i = 0; i < C::IPT; ++i) {
+            for (int i = 0; i < IPT; ++i) {
                 int j = prod_upto + tid + i * C::CONSUMERS;
                 if (j < y_need) {
                     int p = (j + shift_v) & (C::RN - 1);
@@ -393,75 +497,88 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         fence_proxy_async();  // ring slots written here are later overwritten by bulk copies
         named_bar_sync(1, C::CONSUMERS);
 
-        // ---- phase B: per-thread merge walk + segmented scan -------------------------------------
-        auto row_end = [&](int i) {
-            return i < nrows_max ? sm.row[(tx0 + i + 1 + shift_r) & (C::RR - 1)] : INT_MAX;
-        };
-        auto prod = [&](int j) { return sm.val[(ty0 + j + shift_v) & (C::RN - 1)]; };
-        const int nnz_max = y_need - ty0;
-        Seg<T> elem;
-        int head_row;
-        T head_val;
-        {
-            // thread_merge_walk, plus capture of the coordinate where the tile ends
-            int diag = min(tid * C::IPT, items);
-            int2 c = merge_path_search(diag, row_end, nrows_max, nnz_max, ty0);
-            int rx = c.x, ny = ty0 + c.y;
-            int cur_end = row_end(rx);
-            T running = T(0);
-            elem.ended = 0;
-            head_row = 0;
-            head_val = T(0);
+        // ---- phase B -------------------------------------------------------------------------------
+        // clear the other bitmap for the next tile (its last readers finished before the barrier)
+        if (tid < C::BW) sm.bits[buf ^ 1][tid] = 0u;
+
+        // my IPT flag bits and the number of row ends before my first item (= my start row offset)
+        const int diag = tid * IPT;
+        const uint32_t w0 = bits_w[diag >> 5], w1 = bits_w[(diag >> 5) + 1];
+        const uint32_t bits = __funnelshift_r(w0, w1, diag & 31) & ((1u << IPT) - 1u);
+        const int cnt = __popc(bits);
+        int before_warp = 0, all = 0;
 #pragma unroll
-            for (int i = 0; i < C::IPT; ++i) {
-                if (diag + i < items) {
-                    if (ny < cur_end) {
-                        running += prod(ny - ty0);
-                        ++ny;
-                    } else {
-                        if (!elem.ended) {
-                            elem.ended = 1;
-                            head_row = rx;
-                            head_val = running;
-                        } else {
-                            sm.y[rx] = running;
-                        }
-                        running = T(0);
-                        ++rx;
-                        cur_end = row_end(rx);
-                    }
-                }
-            }
-            elem.val = running;
-            if (diag < items && diag + C::IPT >= items) sm.tile_end = make_int2(tx0 + rx, ny);
+        for (int k = lane; k < C::BW; k += 32) {
+            int pc = __popc(bits_w[k]);
+            all += pc;
+            if (k < warp * IPT) before_warp += pc;   // warp w owns bitmap words [w*IPT, (w+1)*IPT)
         }
+        before_warp = __reduce_add_sync(kFull, before_warp);
+        const int nrows = __reduce_add_sync(kFull, all);
+        int inc = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            int v = __shfl_up_sync(kFull, inc, s);
+            if (lane >= s) inc += v;
+        }
+        const int xs = before_warp + inc - cnt;      // row ends before my span == my start row - x0
+
+        // serial walk over my IPT merge items (cpu_spmv.cpp:324-340; agent_spmv_orig.cuh:557-578):
+        // flag bit -> the row ends here, else consume the next product.  Loads depend only on the
+        // flag bits, so they all issue up front.
+        const int my_items = min(max(items - diag, 0), IPT);
+        int ny = y0 + diag - xs;                     // my first nonzero (absolute index)
+        T sums[IPT];
+        T running = T(0);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const bool is_end = (bits >> i) & 1u;
+            T v = T(0);
+            if (!is_end && i < my_items) v = sm.val[(ny + shift_v) & (C::RN - 1)];
+            ny += is_end ? 0 : 1;
+            running += v;
+            sums[i] = running;
+            if (is_end) running = T(0);
+        }
+        Seg<T> elem;
+        elem.val = running;
+        elem.ended = cnt > 0;
         Seg<T> excl, total;
         block_seg_scan_exclusive<T, NCW>(elem, carry, sm.warp, tid, 1, excl, total);
-        if (elem.ended) sm.y[head_row] = head_val + excl.val;
-        named_bar_sync(1, C::CONSUMERS);
 
-        // ---- tile epilogue: coalesced y store, advance, release dead ring chunks ---------------
-        const int2 te = sm.tile_end;
-        const int nrows = te.x - tx0;
-        for (int r = tid; r < nrows; r += C::CONSUMERS)
-            y[tx0 + r] = epilogue<T, AXPBY>(sm.y[r], alpha, beta, y + tx0 + r);
+        // finished rows straight to y: my k-th row end is row x0 + xs + k; the first one also
+        // collects what earlier threads / tiles accumulated for that row
+        {
+            int row = x0 + xs;
+            T add = excl.val;
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                if ((bits >> i) & 1u) {
+                    y[row] = epilogue<T, AXPBY>(sums[i] + add, alpha, beta, y + row);
+                    add = T(0);
+                    ++row;
+                }
+            }
+        }
 
+        // ---- advance; release ring chunks that are now entirely behind the tile end -----------------
+        x0 += nrows;
+        y0 += items - nrows;
+        d += items;
+        carry.val = total.val;
+        carry.ended = 0;
+        buf ^= 1;
         if (tid == 0) {
-            while (n_released < n_waited && (int64_t)(kn_lo + n_released + 1) * C::CH <= te.y) {
+            while (n_released < n_waited && (int64_t)(kn_lo + n_released + 1) * C::CH <= y0) {
                 mbar_arrive(&sm.empty_n[n_released % C::NSLOT]);
                 ++n_released;
             }
-            // row chunk k holds j in [k*RCH, (k+1)*RCH); rows < te.x are dead, i.e. j <= te.x
-            while (r_released < r_waited && (int64_t)(kr_lo + r_released + 1) * C::RCH <= te.x + 1) {
+            // row chunk k holds j in [k*RCH, (k+1)*RCH); rows < x0 are dead, i.e. j <= x0
+            while (r_released < r_waited && (int64_t)(kr_lo + r_released + 1) * C::RCH <= x0 + 1) {
                 mbar_arrive(&sm.empty_r[r_released % C::RSLOT]);
                 ++r_released;
             }
         }
-        carry.val = total.val;
-        carry.ended = 0;
-        tx0 = te.x;
-        ty0 = te.y;
-        d += items;
     }
 
     // swath carry-out (cpu_spmv.cpp:343-344): the row that continues into the next swath
@@ -476,19 +593,20 @@ static int stream_launch(const StreamGeom& g, const T* values, const int* row_of
                          const T* x, T* y, int num_rows, int num_nonzeros, int2* swath_coords,
                          int* carry_rows, T* carry_vals, T alpha, T beta, cudaStream_t stream)
 {
-    auto kernel = spmv_stream_kernel<T, AXPBY>;
-    static bool configured[64] = {};  // per template instantiation and device
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return (int)e;
-    if (!configured[dev & 63]) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
-        if (e != cudaSuccess) return (int)e;
-        configured[dev & 63] = true;
-    }
     int shift_v = (int)((reinterpret_cast<uintptr_t>(values) & 15) / sizeof(T));
     int shift_c = (int)((reinterpret_cast<uintptr_t>(col) & 15) / sizeof(int));
     int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
+    const bool vec = shift_v == 0 && shift_c == 0;
+    auto kernel = vec ? spmv_stream_kernel<T, AXPBY, true> : spmv_stream_kernel<T, AXPBY, false>;
+    static bool configured[2][64] = {};  // per template instantiation, variant and device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (!configured[vec][dev & 63]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        configured[vec][dev & 63] = true;
+    }
     kernel<<<g.num_swaths, g.threads, g.smem_bytes, stream>>>(values, row_offsets, col, x, y, num_rows,
                                                               num_nonzeros, g.swath_items, swath_coords,
                                                               carry_rows, carry_vals, alpha, beta,
