@@ -15,12 +15,16 @@
 //           unrolled loop driven by its IPT flag bits.  Partial rows are closed by a warp-shuffle
 //           segmented scan; finished rows are written to y straight from registers.
 //
-// Data movement: a dedicated producer warp streams the swath's values / column indices and its
-// row offsets into two shared-memory rings with cp.async.bulk (TMA, SASS UBLKCP) completing on
-// mbarriers; ring slots are fixed-size chunks of the *absolute* index space, so every bulk copy
-// is 16-byte aligned no matter where the swath starts (ragged ends of the first/last chunk, and
-// arrays whose base is not 16-byte aligned, are patched with a handful of scalar copies by the
-// same warp).  Consumers never wait on HBM for the stream, only on L2 for the x gathers.
+// Three warp-specialised pipeline stages per block, decoupled by mbarriers over a deep shared-
+// memory ring (chunks of the *absolute* nonzero index space, so every bulk copy is 16-byte
+// aligned no matter where the swath starts; ragged ends of the first/last chunk and arrays whose
+// base is not 16-byte aligned are patched with a handful of scalar copies):
+//   1. producer warp   cp.async.bulk (TMA, SASS UBLKCP) of values / column indices / row offsets
+//                      -> full_raw[chunk]
+//   2. gather warps    wait full_raw; LDS.128 column indices, LDG x[col], multiply in place
+//                      -> full_prod[chunk].  They run several chunks ahead of stage 3, so the
+//                      L2 latency of the x gathers overlaps the reduction of earlier tiles.
+//   3. reduce warps    wait full_prod; bitmap / walk / scan / y stores; -> empty[chunk]
 #pragma once
 
 #include <limits.h>
@@ -109,21 +113,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 struct StreamCfg {
-    static constexpr int CONSUMERS = 256;                      // 8 consumer warps
-    static constexpr int THREADS = CONSUMERS + 32;             // + 1 producer warp
+    static constexpr int REDUCERS = 128;                       // 4 reduce warps
+    static constexpr int GATHERERS = 128;                      // 4 gather warps
+    static constexpr int THREADS = REDUCERS + GATHERERS + 32;  // + 1 producer warp
     static constexpr int IPT = 9;                              // odd: conflict-free strided smem walk
-    static constexpr int TILE = CONSUMERS * IPT;
-    static constexpr int CH = 512;                             // nonzeros per ring chunk
-    static constexpr int NSLOT = 8;                            // chunks in the nonzero ring
+    static constexpr int TILE = REDUCERS * IPT;
+    static constexpr int CH = GATHERERS * 4;                   // nonzeros per ring chunk: one aligned group of 4 per gather thread
+    static constexpr int NSLOT = 16;                           // chunks in the nonzero ring
     static constexpr int RN = CH * NSLOT;                      // ring capacity (power of two)
-    static constexpr int RCH = 512;                            // row offsets per ring chunk
+    static constexpr int GU = 2;                               // chunks a gather warp keeps in flight
+    static constexpr int RCH = 256;                            // row offsets per ring chunk
     static constexpr int RSLOT = 8;
     static constexpr int RR = RCH * RSLOT;
     static constexpr int BW = TILE / 32 + 2;                   // words per row-end bitmap
-    static constexpr int CTAS_PER_SM = 3;
+    static constexpr int CTAS_PER_SM = sizeof(T) == 8 ? 2 : 3;
     static constexpr int MIN_SWATH = 1024;                     // merge items; small inputs use fewer blocks
     static_assert((RN & (RN - 1)) == 0 && (RR & (RR - 1)) == 0, "rings are power-of-two sized");
-    static_assert(RN >= TILE + 2 * CH && RR >= TILE + 1 + 2 * RCH, "ring must hold one tile plus slack");
+    static_assert(RN >= TILE + (GU + 3) * CH && RR >= TILE + 1 + 2 * RCH, "ring must hold one tile plus slack");
     static_assert(TILE % 32 == 0 && BW <= 96 && (IPT & 1) == 1 && IPT < 32, "bitmap layout");
 };
 
@@ -134,9 +140,10 @@ struct StreamSmem {
     alignas(128) int col[C::RN];
     alignas(128) int row[C::RR];      // row_offsets entries (index j = row + 1)
     alignas(16) uint32_t bits[2][C::BW];  // row-end flags per merge item, double-buffered
-    alignas(16) Seg<T> warp[C::CONSUMERS / 32];
-    alignas(8) uint64_t full_n[C::NSLOT];
-    uint64_t empty_n[C::NSLOT];
+    alignas(16) Seg<T> warp[C::REDUCERS / 32];
+    alignas(8) uint64_t full_raw[C::NSLOT];   // TMA landed
+    uint64_t full_prod[C::NSLOT];             // products written by the gather warps
+    uint64_t empty_n[C::NSLOT];               // reduce warps are past this chunk
     uint64_t full_r[C::RSLOT];
     uint64_t empty_r[C::RSLOT];
     int2 swath[2];                    // start / end coordinate of this block's swath
@@ -272,8 +279,8 @@ struct Vec4<double> {
 };
 
 // ------------------------------------------------------------------------------------------------
-// The kernel.  VEC: values/column_indices bases are 16-byte aligned, so phase A works on aligned
-// groups of four nonzeros with 128-bit shared-memory accesses.
+// The kernel.  VEC: values/column_indices bases are 16-byte aligned, so the gather stage works on
+// aligned groups of four nonzeros with 128-bit shared-memory accesses.
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool AXPBY, bool VEC>
 __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) void spmv_stream_kernel(
@@ -283,7 +290,8 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     T* __restrict__ carry_vals, T alpha, T beta, int shift_v, int shift_c, int shift_r)
 {
     using C = StreamCfg<T>;
-    constexpr int NCW = C::CONSUMERS / 32;
+    constexpr int NRW = C::REDUCERS / 32;   // reduce warps: 0 .. NRW-1
+    constexpr int NGW = C::GATHERERS / 32;  // gather warps: NRW .. NRW+NGW-1; producer: NRW+NGW
     constexpr int IPT = C::IPT;
     extern __shared__ unsigned char smem_raw[];
     StreamSmem<T>& sm =
@@ -299,9 +307,10 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     const int* __restrict__ row_end_offsets = row_offsets + 1;
 
     // ---- prologue: barriers, bitmaps, the two swath boundary searches (warps 0 and 1) ----------
-    if (tid == C::CONSUMERS) {
+    if (tid == C::THREADS - 32) {
         for (int i = 0; i < C::NSLOT; ++i) {
-            mbar_init(&sm.full_n[i], 1);
+            mbar_init(&sm.full_raw[i], 1);
+            mbar_init(&sm.full_prod[i], NGW);
             mbar_init(&sm.empty_n[i], 1);
         }
         for (int i = 0; i < C::RSLOT; ++i) {
@@ -333,8 +342,8 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     const int kr_lo = J0 / C::RCH;
     const int kr_hi = J1 > J0 ? (J1 - 1) / C::RCH + 1 : kr_lo;
 
-    if (warp == NCW) {
-        // =================================== producer warp =====================================
+    if (warp == NRW + NGW) {
+        // =================================== stage 1: producer warp ============================
         const uint64_t policy = l2_policy_evict_first();
         int kn = kn_lo, kr = kr_lo;
         while (kn < kn_hi || kr < kr_hi) {
@@ -349,13 +358,13 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
                 if (free_slot) {
                     int lo = max(kn * C::CH, Y0), hi = (int)min((int64_t)(kn + 1) * C::CH, (int64_t)Y1);
                     uint32_t b = stage_range<T>(values, shift_v, lo, hi, sm.val, C::RN - 1,
-                                                &sm.full_n[slot], policy, lane);
+                                                &sm.full_raw[slot], policy, lane);
                     b += stage_range<int>(column_indices, shift_c, lo, hi, sm.col, C::RN - 1,
-                                          &sm.full_n[slot], policy, lane);
+                                          &sm.full_raw[slot], policy, lane);
                     __syncwarp();
                     if (lane == 0) {
-                        if (b) mbar_arrive_expect_tx(&sm.full_n[slot], b);
-                        else mbar_arrive(&sm.full_n[slot]);
+                        if (b) mbar_arrive_expect_tx(&sm.full_raw[slot], b);
+                        else mbar_arrive(&sm.full_raw[slot]);
                     }
                     ++kn;
                     progress = true;
@@ -386,10 +395,99 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         return;
     }
 
-    // ===================================== consumer warps ======================================
+    if (warp >= NRW) {
+        // =================================== stage 2: gather warps =============================
+        // products value * x[col] in place in the value ring (agent_spmv_orig.cuh:472-494), GU
+        // chunks at a time so every thread keeps 4*GU gathers in flight
+        const int gt = tid - C::REDUCERS;  // 0 .. GATHERERS-1
+        for (int k0 = kn_lo; k0 < kn_hi; k0 += C::GU) {
+            if (VEC) {
+                int4 cg[C::GU];
+#pragma unroll
+                for (int u = 0; u < C::GU; ++u) {
+                    const int k = k0 + u;
+                    if (k < kn_hi) {
+                        const int kk = k - kn_lo;
+                        mbar_wait(&sm.full_raw[kk % C::NSLOT], (kk / C::NSLOT) & 1);
+                        const int j = k * C::CH + 4 * gt;
+                        int4 c = *reinterpret_cast<const int4*>(&sm.col[j & (C::RN - 1)]);
+                        if (j < Y0 || j + 4 > Y1) {  // swath edge: slots outside [Y0, Y1) hold no data
+                            if (j + 0 < Y0 || j + 0 >= Y1) c.x = 0;
+                            if (j + 1 < Y0 || j + 1 >= Y1) c.y = 0;
+                            if (j + 2 < Y0 || j + 2 >= Y1) c.z = 0;
+                            if (j + 3 < Y0 || j + 3 >= Y1) c.w = 0;
+                        }
+                        cg[u] = c;
+                    } else {
+                        cg[u] = make_int4(0, 0, 0, 0);
+                    }
+                }
+                T xg[C::GU][4];
+#pragma unroll
+                for (int u = 0; u < C::GU; ++u) {
+                    if (k0 + u < kn_hi) {
+                        xg[u][0] = __ldg(x + cg[u].x);
+                        xg[u][1] = __ldg(x + cg[u].y);
+                        xg[u][2] = __ldg(x + cg[u].z);
+                        xg[u][3] = __ldg(x + cg[u].w);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < C::GU; ++u) {
+                    const int k = k0 + u;
+                    if (k < kn_hi) {
+                        const int j = k * C::CH + 4 * gt;
+                        T* p = &sm.val[j & (C::RN - 1)];
+                        Vec4<T> v;
+                        v.load(p);
+                        v.mul(xg[u][0], xg[u][1], xg[u][2], xg[u][3]);
+                        v.store(p);
+                    }
+                }
+            } else {
+                int cidx[C::GU][4];
+                T xv[C::GU][4];
+#pragma unroll
+                for (int u = 0; u < C::GU; ++u) {
+                    const int k = k0 + u;
+                    if (k < kn_hi) {
+                        const int kk = k - kn_lo;
+                        mbar_wait(&sm.full_raw[kk % C::NSLOT], (kk / C::NSLOT) & 1);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = k * C::CH + gt + e * C::GATHERERS;
+                        cidx[u][e] = (k < kn_hi && j >= Y0 && j < Y1) ? sm.col[(j + shift_c) & (C::RN - 1)] : -1;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < C::GU; ++u)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) xv[u][e] = cidx[u][e] >= 0 ? __ldg(x + cidx[u][e]) : T(0);
+#pragma unroll
+                for (int u = 0; u < C::GU; ++u)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (cidx[u][e] >= 0) {
+                            const int j = (k0 + u) * C::CH + gt + e * C::GATHERERS;
+                            const int p = (j + shift_v) & (C::RN - 1);
+                            sm.val[p] = sm.val[p] * xv[u][e];
+                        }
+            }
+            fence_proxy_async();  // these generic writes are later overwritten by bulk copies
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int u = 0; u < C::GU; ++u)
+                    if (k0 + u < kn_hi) mbar_arrive(&sm.full_prod[(k0 + u - kn_lo) % C::NSLOT]);
+            }
+        }
+        return;
+    }
+
+    // ===================================== stage 3: reduce warps ===============================
     int x0 = X0, y0 = Y0;                            // current tile start coordinate
     int d = d_begin;                                 // current diagonal
-    int prod_upto = VEC ? (Y0 & ~3) : Y0;            // products exist for nonzeros [.., prod_upto)
     int n_waited = 0, r_waited = 0;                  // chunks (relative index) already acquired
     int n_released = 0, r_released = 0;
     int buf = 0;
@@ -403,13 +501,6 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         const int nrows_max = min(items, X1 - x0);   // row ends this tile can contain
 
         // ---- acquire the ring chunks this tile can touch ---------------------------------------
-        if (y_need > Y0) {
-            int kk_need = (y_need - 1) / C::CH - kn_lo;
-            while (n_waited <= kk_need) {
-                mbar_wait(&sm.full_n[n_waited % C::NSLOT], (n_waited / C::NSLOT) & 1);
-                ++n_waited;
-            }
-        }
         if (nrows_max > 0) {
             int kk_need = (x0 + nrows_max) / C::RCH - kr_lo;  // j = x0 + nrows_max is the last needed
             while (r_waited <= kk_need) {
@@ -420,84 +511,21 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
 
         // ---- row-end flags: merge item p = row_end[r] - y0 + (r - x0) is the end of row r --------
         uint32_t* bits_w = sm.bits[buf];
-        for (int r = tid; r < nrows_max; r += C::CONSUMERS) {
+        for (int r = tid; r < nrows_max; r += C::REDUCERS) {
             int e = sm.row[(x0 + r + 1 + shift_r) & (C::RR - 1)];
             int pos = e - y0 + r;
             if (pos >= items) break;                 // positions increase with r
             atomicOr(&bits_w[pos >> 5], 1u << (pos & 31));
         }
-
-        // ---- phase A: products for the not-yet-multiplied nonzeros (agent_spmv_orig.cuh:472-494) --
-        if (VEC) {
-            // aligned groups of four nonzeros; two groups per thread in flight, then the remainder
-            constexpr int GROUPS = (C::TILE / 4 + 1 + C::CONSUMERS - 1) / C::CONSUMERS;
-            const int pa_hi = (y_need + 3) & ~3;
-            auto load_cols = [&](int j) {
-                int4 c = *reinterpret_cast<const int4*>(&sm.col[j & (C::RN - 1)]);
-                if (j < Y0 || j + 4 > Y1) {          // swath edge: slots outside [Y0, Y1) hold no data
-                    if (j + 0 < Y0 || j + 0 >= Y1) c.x = 0;
-                    if (j + 1 < Y0 || j + 1 >= Y1) c.y = 0;
-                    if (j + 2 < Y0 || j + 2 >= Y1) c.z = 0;
-                    if (j + 3 < Y0 || j + 3 >= Y1) c.w = 0;
-                }
-                return c;
-            };
-            auto finish = [&](int j, T a, T b, T c, T dd) {
-                T* p = &sm.val[j & (C::RN - 1)];
-                Vec4<T> v;
-                v.load(p);
-                v.mul(a, b, c, dd);
-                v.store(p);
-            };
-#pragma unroll
-            for (int g0 = 0; g0 < GROUPS; g0 += 2) {
-                const int ja = prod_upto + 4 * (tid + g0 * C::CONSUMERS);
-                const int jb = ja + 4 * C::CONSUMERS;
-                const bool has_a = ja < pa_hi, has_b = (g0 + 1 < GROUPS) && jb < pa_hi;
-                int4 ca = make_int4(0, 0, 0, 0), cb = make_int4(0, 0, 0, 0);
-                if (has_a) ca = load_cols(ja);
-                if (has_b) cb = load_cols(jb);
-                T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0), b0 = T(0), b1 = T(0), b2 = T(0), b3 = T(0);
-                if (has_a) {
-                    a0 = __ldg(x + ca.x);
-                    a1 = __ldg(x + ca.y);
-                    a2 = __ldg(x + ca.z);
-                    a3 = __ldg(x + ca.w);
-                }
-                if (has_b) {
-                    b0 = __ldg(x + cb.x);
-                    b1 = __ldg(x + cb.y);
-                    b2 = __ldg(x + cb.z);
-                    b3 = __ldg(x + cb.w);
-                }
-                if (has_a) finish(ja, a0, a1, a2, a3);
-                if (has_b) finish(jb, b0, b1, b2, b3);
+        if (y_need > Y0) {
+            int kk_need = (y_need - 1) / C::CH - kn_lo;
+            while (n_waited <= kk_need) {
+                mbar_wait(&sm.full_prod[n_waited % C::NSLOT], (n_waited / C::NSLOT) & 1);
+                ++n_waited;
             }
-            prod_upto = max(prod_upto, pa_hi);
-        } else {
-            int cidx[IPT];
-            T xv[IPT];
-#pragma unroll
-            for (int i = 0; i < IPT; ++i) {
-                int j = prod_upto + tid + i * C::CONSUMERS;
-                cidx[i] = j < y_need ? sm.col[(j + shift_c) & (C::RN - 1)] : -1;
-            }
-#pragma unroll
-            for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? __ldg(x + cidx[i]) : T(0);
-#pragma unroll
-            for (int i = 0; i < IPT; ++i) {
-                int j = prod_upto + tid + i * C::CONSUMERS;
-                if (j < y_need) {
-                    int p = (j + shift_v) & (C::RN - 1);
-                    sm.val[p] = sm.val[p] * xv[i];
-                }
-            }
-            prod_upto = max(prod_upto, y_need);
         }
-        fence_proxy_async();  // ring slots written here are later overwritten by bulk copies
-        named_bar_sync(1, C::CONSUMERS);
+        named_bar_sync(1, C::REDUCERS);
 
-        // ---- phase B -------------------------------------------------------------------------------
         // clear the other bitmap for the next tile (its last readers finished before the barrier)
         if (tid < C::BW) sm.bits[buf ^ 1][tid] = 0u;
 
@@ -544,7 +572,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         elem.val = running;
         elem.ended = cnt > 0;
         Seg<T> excl, total;
-        block_seg_scan_exclusive<T, NCW>(elem, carry, sm.warp, tid, 1, excl, total);
+        block_seg_scan_exclusive<T, NRW>(elem, carry, sm.warp, tid, 1, excl, total);
 
         // finished rows straight to y: my k-th row end is row x0 + xs + k; the first one also
         // collects what earlier threads / tiles accumulated for that row
