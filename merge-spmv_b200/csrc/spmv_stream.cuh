@@ -21,10 +21,13 @@
 // base is not 16-byte aligned are patched with a handful of scalar copies):
 //   1. producer warp   cp.async.bulk (TMA, SASS UBLKCP) of values / column indices / row offsets
 //                      -> full_raw[chunk]
-//   2. gather warps    wait full_raw; LDS.128 column indices, LDG x[col], multiply in place
-//                      -> full_prod[chunk].  They run several chunks ahead of stage 3, so the
-//                      L2 latency of the x gathers overlaps the reduction of earlier tiles.
-//   3. reduce warps    wait full_prod; bitmap / walk / scan / y stores; -> empty[chunk]
+//   2. gather warps    wait full_raw; LDS.128 column indices, then one 4/8-byte cp.async
+//                      (LDGSTS) per nonzero copies x[col] straight into an x ring -- no
+//                      registers are held while the gather is in flight, so thousands of L2
+//                      requests per SM stay outstanding -> full_x[chunk] when they have landed.
+//                      (fp32: x[col] overwrites col in place; fp64 has a separate ring.)
+//   3. reduce warps    wait full_x; bitmap / walk with fma(value, x, sum) / scan / y stores
+//                      -> empty[chunk]
 #pragma once
 
 #include <limits.h>
@@ -99,6 +102,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// 4- or 8-byte asynchronous global -> shared copy (LDGSTS): the x gather, no register staging
+template <int BYTES>
+__device__ __forceinline__ void cp_async_gather(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "n"(BYTES)
+                 : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (counted in the
+// barrier's expected arrivals: .noinc)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -115,13 +132,12 @@ template <typename T>
 struct StreamCfg {
     static constexpr int REDUCERS = 128;                       // 4 reduce warps
     static constexpr int GATHERERS = 128;                      // 4 gather warps
-    static constexpr int THREADS = REDUCERS + GATHERERS + 32;  // + 1 producer warp
+    static constexpr int THREADS = REDUCERS + GATHERERS + 64;  // + 2 producer warps (nonzeros, row offsets)
     static constexpr int IPT = 9;                              // odd: conflict-free strided smem walk
     static constexpr int TILE = REDUCERS * IPT;
     static constexpr int CH = GATHERERS * 4;                   // nonzeros per ring chunk: one aligned group of 4 per gather thread
-    static constexpr int NSLOT = 16;                           // chunks in the nonzero ring
+    static constexpr int NSLOT = sizeof(T) == 8 ? 8 : 16;      // chunks in the nonzero ring
     static constexpr int RN = CH * NSLOT;                      // ring capacity (power of two)
-    static constexpr int GU = 2;                               // chunks a gather warp keeps in flight
     static constexpr int RCH = 256;                            // row offsets per ring chunk
     static constexpr int RSLOT = 8;
     static constexpr int RR = RCH * RSLOT;
@@ -129,20 +145,22 @@ struct StreamCfg {
     static constexpr int CTAS_PER_SM = sizeof(T) == 8 ? 2 : 3;
     static constexpr int MIN_SWATH = 1024;                     // merge items; small inputs use fewer blocks
     static_assert((RN & (RN - 1)) == 0 && (RR & (RR - 1)) == 0, "rings are power-of-two sized");
-    static_assert(RN >= TILE + (GU + 3) * CH && RR >= TILE + 1 + 2 * RCH, "ring must hold one tile plus slack");
+    static_assert((NSLOT & (NSLOT - 1)) == 0 && (RSLOT & (RSLOT - 1)) == 0, "slot counts are powers of two");
+    static_assert(RN >= TILE + 3 * CH && RR >= TILE + 1 + 2 * RCH, "ring must hold one tile plus slack");
     static_assert(TILE % 32 == 0 && BW <= 96 && (IPT & 1) == 1 && IPT < 32, "bitmap layout");
 };
 
 template <typename T>
 struct StreamSmem {
     using C = StreamCfg<T>;
-    alignas(128) T val[C::RN];        // values, overwritten in place by value*x[col]
-    alignas(128) int col[C::RN];
+    alignas(128) T val[C::RN];        // values
+    alignas(128) int col[C::RN];      // column indices; fp32: overwritten in place by x[col]
+    alignas(128) T xg[sizeof(T) == 8 ? C::RN : 4];  // fp64: gathered x[col]
     alignas(128) int row[C::RR];      // row_offsets entries (index j = row + 1)
     alignas(16) uint32_t bits[2][C::BW];  // row-end flags per merge item, double-buffered
     alignas(16) Seg<T> warp[C::REDUCERS / 32];
     alignas(8) uint64_t full_raw[C::NSLOT];   // TMA landed
-    uint64_t full_prod[C::NSLOT];             // products written by the gather warps
+    uint64_t full_x[C::NSLOT];                // x[col] gathers of the chunk have landed
     uint64_t empty_n[C::NSLOT];               // reduce warps are past this chunk
     uint64_t full_r[C::RSLOT];
     uint64_t empty_r[C::RSLOT];
@@ -310,7 +328,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     if (tid == C::THREADS - 32) {
         for (int i = 0; i < C::NSLOT; ++i) {
             mbar_init(&sm.full_raw[i], 1);
-            mbar_init(&sm.full_prod[i], NGW);
+            mbar_init(&sm.full_x[i], C::GATHERERS);
             mbar_init(&sm.empty_n[i], 1);
         }
         for (int i = 0; i < C::RSLOT; ++i) {
@@ -343,144 +361,99 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     const int kr_hi = J1 > J0 ? (J1 - 1) / C::RCH + 1 : kr_lo;
 
     if (warp == NRW + NGW) {
-        // =================================== stage 1: producer warp ============================
+        // ======================= stage 1a: producer warp, values + column indices ==============
+        // Interior chunks of 16-byte-aligned arrays are two bulk copies issued by lane 0 with a
+        // handful of instructions; the (possibly ragged) first and last chunk of the swath, and
+        // arrays with misaligned bases, take the general whole-warp path.
         const uint64_t policy = l2_policy_evict_first();
-        int kn = kn_lo, kr = kr_lo;
-        while (kn < kn_hi || kr < kr_hi) {
-            bool progress = false;
-            if (kn < kn_hi) {
-                int kk = kn - kn_lo, slot = kk % C::NSLOT, use = kk / C::NSLOT;
-                bool free_slot = true;
-                if (use > 0) {
-                    if (lane == 0) free_slot = mbar_test_wait(&sm.empty_n[slot], (use - 1) & 1);
-                    free_slot = __shfl_sync(kFull, free_slot, 0);
+        const bool aligned = (shift_v | shift_c) == 0;
+        constexpr uint32_t kChunkBytes = C::CH * (uint32_t)(sizeof(T) + sizeof(int));
+        for (int kn = kn_lo; kn < kn_hi; ++kn) {
+            const int kk = kn - kn_lo, slot = kk & (C::NSLOT - 1), use = kk / C::NSLOT;
+            if (aligned && kn > kn_lo && kn + 1 < kn_hi) {
+                if (lane == 0) {
+                    if (use > 0) mbar_wait(&sm.empty_n[slot], (use - 1) & 1);
+                    const int pos = (kn & (C::NSLOT - 1)) * C::CH;
+                    mbar_arrive_expect_tx(&sm.full_raw[slot], kChunkBytes);
+                    bulk_g2s(&sm.val[pos], values + (size_t)kn * C::CH, C::CH * (uint32_t)sizeof(T),
+                             &sm.full_raw[slot], policy);
+                    bulk_g2s(&sm.col[pos], column_indices + (size_t)kn * C::CH, C::CH * (uint32_t)sizeof(int),
+                             &sm.full_raw[slot], policy);
                 }
-                if (free_slot) {
-                    int lo = max(kn * C::CH, Y0), hi = (int)min((int64_t)(kn + 1) * C::CH, (int64_t)Y1);
-                    uint32_t b = stage_range<T>(values, shift_v, lo, hi, sm.val, C::RN - 1,
-                                                &sm.full_raw[slot], policy, lane);
-                    b += stage_range<int>(column_indices, shift_c, lo, hi, sm.col, C::RN - 1,
-                                          &sm.full_raw[slot], policy, lane);
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (b) mbar_arrive_expect_tx(&sm.full_raw[slot], b);
-                        else mbar_arrive(&sm.full_raw[slot]);
-                    }
-                    ++kn;
-                    progress = true;
-                }
-            }
-            if (kr < kr_hi) {
-                int kk = kr - kr_lo, slot = kk % C::RSLOT, use = kk / C::RSLOT;
-                bool free_slot = true;
-                if (use > 0) {
-                    if (lane == 0) free_slot = mbar_test_wait(&sm.empty_r[slot], (use - 1) & 1);
-                    free_slot = __shfl_sync(kFull, free_slot, 0);
-                }
-                if (free_slot) {
-                    int lo = max(kr * C::RCH, J0), hi = (int)min((int64_t)(kr + 1) * C::RCH, (int64_t)J1);
-                    uint32_t b = stage_range<int>(row_offsets, shift_r, lo, hi, sm.row, C::RR - 1,
-                                                  &sm.full_r[slot], policy, lane);
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (b) mbar_arrive_expect_tx(&sm.full_r[slot], b);
-                        else mbar_arrive(&sm.full_r[slot]);
-                    }
-                    ++kr;
-                    progress = true;
+            } else {
+                __syncwarp();
+                if (use > 0) mbar_wait(&sm.empty_n[slot], (use - 1) & 1);
+                int lo = max(kn * C::CH, Y0), hi = (int)min((int64_t)(kn + 1) * C::CH, (int64_t)Y1);
+                uint32_t b = stage_range<T>(values, shift_v, lo, hi, sm.val, C::RN - 1, &sm.full_raw[slot],
+                                            policy, lane);
+                b += stage_range<int>(column_indices, shift_c, lo, hi, sm.col, C::RN - 1, &sm.full_raw[slot],
+                                      policy, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    if (b) mbar_arrive_expect_tx(&sm.full_raw[slot], b);
+                    else mbar_arrive(&sm.full_raw[slot]);
                 }
             }
-            if (!progress) __nanosleep(64);
+        }
+        return;
+    }
+    if (warp == NRW + NGW + 1) {
+        // ======================= stage 1b: producer warp, row offsets ===========================
+        const uint64_t policy = l2_policy_evict_first();
+        for (int kr = kr_lo; kr < kr_hi; ++kr) {
+            const int kk = kr - kr_lo, slot = kk & (C::RSLOT - 1), use = kk / C::RSLOT;
+            if (use > 0) mbar_wait(&sm.empty_r[slot], (use - 1) & 1);
+            int lo = max(kr * C::RCH, J0), hi = (int)min((int64_t)(kr + 1) * C::RCH, (int64_t)J1);
+            uint32_t b = stage_range<int>(row_offsets, shift_r, lo, hi, sm.row, C::RR - 1, &sm.full_r[slot],
+                                          policy, lane);
+            __syncwarp();
+            if (lane == 0) {
+                if (b) mbar_arrive_expect_tx(&sm.full_r[slot], b);
+                else mbar_arrive(&sm.full_r[slot]);
+            }
         }
         return;
     }
 
+    // where the gathered x of nonzero j lives: fp64 -> xg ring, fp32 -> in place of its column index
+    auto x_slot = [&](int j) -> T* {
+        if (sizeof(T) == 8) return &sm.xg[j & (C::RN - 1)];
+        return reinterpret_cast<T*>(&sm.col[(j + shift_c) & (C::RN - 1)]);
+    };
+
     if (warp >= NRW) {
-        // =================================== stage 2: gather warps =============================
-        // products value * x[col] in place in the value ring (agent_spmv_orig.cuh:472-494), GU
-        // chunks at a time so every thread keeps 4*GU gathers in flight
+        // =================================== stage 2: gather warps (NRW .. NRW+NGW-1) ==========
+        // x[col] of every nonzero of the chunk by asynchronous 4/8-byte copies
+        // (the gather of agent_spmv_orig.cuh:472-494, without the register round trip)
         const int gt = tid - C::REDUCERS;  // 0 .. GATHERERS-1
-        for (int k0 = kn_lo; k0 < kn_hi; k0 += C::GU) {
+        for (int k = kn_lo; k < kn_hi; ++k) {
+            const int kk = k - kn_lo, slot = kk & (C::NSLOT - 1);
+            mbar_wait(&sm.full_raw[slot], (kk / C::NSLOT) & 1);
             if (VEC) {
-                int4 cg[C::GU];
-#pragma unroll
-                for (int u = 0; u < C::GU; ++u) {
-                    const int k = k0 + u;
-                    if (k < kn_hi) {
-                        const int kk = k - kn_lo;
-                        mbar_wait(&sm.full_raw[kk % C::NSLOT], (kk / C::NSLOT) & 1);
-                        const int j = k * C::CH + 4 * gt;
-                        int4 c = *reinterpret_cast<const int4*>(&sm.col[j & (C::RN - 1)]);
-                        if (j < Y0 || j + 4 > Y1) {  // swath edge: slots outside [Y0, Y1) hold no data
-                            if (j + 0 < Y0 || j + 0 >= Y1) c.x = 0;
-                            if (j + 1 < Y0 || j + 1 >= Y1) c.y = 0;
-                            if (j + 2 < Y0 || j + 2 >= Y1) c.z = 0;
-                            if (j + 3 < Y0 || j + 3 >= Y1) c.w = 0;
-                        }
-                        cg[u] = c;
-                    } else {
-                        cg[u] = make_int4(0, 0, 0, 0);
-                    }
-                }
-                T xg[C::GU][4];
-#pragma unroll
-                for (int u = 0; u < C::GU; ++u) {
-                    if (k0 + u < kn_hi) {
-                        xg[u][0] = __ldg(x + cg[u].x);
-                        xg[u][1] = __ldg(x + cg[u].y);
-                        xg[u][2] = __ldg(x + cg[u].z);
-                        xg[u][3] = __ldg(x + cg[u].w);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < C::GU; ++u) {
-                    const int k = k0 + u;
-                    if (k < kn_hi) {
-                        const int j = k * C::CH + 4 * gt;
-                        T* p = &sm.val[j & (C::RN - 1)];
-                        Vec4<T> v;
-                        v.load(p);
-                        v.mul(xg[u][0], xg[u][1], xg[u][2], xg[u][3]);
-                        v.store(p);
-                    }
+                const int j = k * C::CH + 4 * gt;
+                const int4 c = *reinterpret_cast<const int4*>(&sm.col[j & (C::RN - 1)]);
+                if (j >= Y0 && j + 4 <= Y1) {
+                    cp_async_gather<sizeof(T)>(x_slot(j + 0), x + c.x);
+                    cp_async_gather<sizeof(T)>(x_slot(j + 1), x + c.y);
+                    cp_async_gather<sizeof(T)>(x_slot(j + 2), x + c.z);
+                    cp_async_gather<sizeof(T)>(x_slot(j + 3), x + c.w);
+                } else {  // swath edge: slots outside [Y0, Y1) hold no data
+                    if (j + 0 >= Y0 && j + 0 < Y1) cp_async_gather<sizeof(T)>(x_slot(j + 0), x + c.x);
+                    if (j + 1 >= Y0 && j + 1 < Y1) cp_async_gather<sizeof(T)>(x_slot(j + 1), x + c.y);
+                    if (j + 2 >= Y0 && j + 2 < Y1) cp_async_gather<sizeof(T)>(x_slot(j + 2), x + c.z);
+                    if (j + 3 >= Y0 && j + 3 < Y1) cp_async_gather<sizeof(T)>(x_slot(j + 3), x + c.w);
                 }
             } else {
-                int cidx[C::GU][4];
-                T xv[C::GU][4];
 #pragma unroll
-                for (int u = 0; u < C::GU; ++u) {
-                    const int k = k0 + u;
-                    if (k < kn_hi) {
-                        const int kk = k - kn_lo;
-                        mbar_wait(&sm.full_raw[kk % C::NSLOT], (kk / C::NSLOT) & 1);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = k * C::CH + gt + e * C::GATHERERS;
-                        cidx[u][e] = (k < kn_hi && j >= Y0 && j < Y1) ? sm.col[(j + shift_c) & (C::RN - 1)] : -1;
+                for (int e = 0; e < 4; ++e) {
+                    const int j = k * C::CH + gt + e * C::GATHERERS;
+                    if (j >= Y0 && j < Y1) {
+                        const int c = sm.col[(j + shift_c) & (C::RN - 1)];
+                        cp_async_gather<sizeof(T)>(x_slot(j), x + c);
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < C::GU; ++u)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) xv[u][e] = cidx[u][e] >= 0 ? __ldg(x + cidx[u][e]) : T(0);
-#pragma unroll
-                for (int u = 0; u < C::GU; ++u)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (cidx[u][e] >= 0) {
-                            const int j = (k0 + u) * C::CH + gt + e * C::GATHERERS;
-                            const int p = (j + shift_v) & (C::RN - 1);
-                            sm.val[p] = sm.val[p] * xv[u][e];
-                        }
             }
-            fence_proxy_async();  // these generic writes are later overwritten by bulk copies
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int u = 0; u < C::GU; ++u)
-                    if (k0 + u < kn_hi) mbar_arrive(&sm.full_prod[(k0 + u - kn_lo) % C::NSLOT]);
-            }
+            cp_async_arrive_noinc(&sm.full_x[slot]);
         }
         return;
     }
@@ -520,7 +493,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         if (y_need > Y0) {
             int kk_need = (y_need - 1) / C::CH - kn_lo;
             while (n_waited <= kk_need) {
-                mbar_wait(&sm.full_prod[n_waited % C::NSLOT], (n_waited / C::NSLOT) & 1);
+                mbar_wait(&sm.full_x[n_waited % C::NSLOT], (n_waited / C::NSLOT) & 1);
                 ++n_waited;
             }
         }
@@ -534,6 +507,8 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         const uint32_t w0 = bits_w[diag >> 5], w1 = bits_w[(diag >> 5) + 1];
         const uint32_t bits = __funnelshift_r(w0, w1, diag & 31) & ((1u << IPT) - 1u);
         const int cnt = __popc(bits);
+        // row ends before my first item: whole words of earlier warps (one REDUX), whole words of my
+        // warp before mine (independent loads), and the low part of my first word
         int before_warp = 0, all = 0;
 #pragma unroll
         for (int k = lane; k < C::BW; k += 32) {
@@ -543,13 +518,11 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         }
         before_warp = __reduce_add_sync(kFull, before_warp);
         const int nrows = __reduce_add_sync(kFull, all);
-        int inc = cnt;
+        int in_warp = __popc(w0 & ((1u << (diag & 31)) - 1u));
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            int v = __shfl_up_sync(kFull, inc, s);
-            if (lane >= s) inc += v;
-        }
-        const int xs = before_warp + inc - cnt;      // row ends before my span == my start row - x0
+        for (int k = 0; k < IPT - 1; ++k)
+            if (warp * IPT + k < (diag >> 5)) in_warp += __popc(bits_w[warp * IPT + k]);
+        const int xs = before_warp + in_warp;        // row ends before my span == my start row - x0
 
         // serial walk over my IPT merge items (cpu_spmv.cpp:324-340; agent_spmv_orig.cuh:557-578):
         // flag bit -> the row ends here, else consume the next product.  Loads depend only on the
@@ -561,10 +534,8 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const bool is_end = (bits >> i) & 1u;
-            T v = T(0);
-            if (!is_end && i < my_items) v = sm.val[(ny + shift_v) & (C::RN - 1)];
+            if (!is_end && i < my_items) running = fma(sm.val[(ny + shift_v) & (C::RN - 1)], *x_slot(ny), running);
             ny += is_end ? 0 : 1;
-            running += v;
             sums[i] = running;
             if (is_end) running = T(0);
         }
@@ -597,6 +568,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
         carry.ended = 0;
         buf ^= 1;
         if (tid == 0) {
+            fence_proxy_async();  // ring slots read/written through the generic proxy are re-filled by bulk copies
             while (n_released < n_waited && (int64_t)(kn_lo + n_released + 1) * C::CH <= y0) {
                 mbar_arrive(&sm.empty_n[n_released % C::NSLOT]);
                 ++n_released;

@@ -369,4 +369,4 @@ def test_launch_counter_and_config():
     ms.csrmv(m.row_offsets, m.col, m.val, x)
     cfg = csrmv_config(8, m.rows, m.nnz)
     assert L.mspmv_launch_count() - before == cfg["kernels_per_call"] == 2
-    assert cfg["threads"] == 288 and cfg["swaths"] <= 4 * torch.cuda.get_device_properties(0).multi_processor_count
+    assert cfg["threads"] % 32 == 0 and cfg["swaths"] <= 4 * torch.cuda.get_device_properties(0).multi_processor_count
