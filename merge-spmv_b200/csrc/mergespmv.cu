@@ -73,20 +73,13 @@ static Engine engine_from_env()
 
 static inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 
-// ---- tile engine geometry -----------------------------------------------------------------
-template <typename T>
-struct TileCfg {
-    static constexpr int THREADS = 256;
-    static constexpr int IPT = sizeof(T) == 8 ? 7 : 9;
-    static constexpr int TILE = THREADS * IPT;
-};
-
 template <typename T>
 struct Plan {
     Engine engine;
     int64_t merge_items;
     int num_tiles;      // tile engine: tiles; stream engine: swaths (threadblocks)
-    size_t off_coords, off_carry_rows, off_carry_vals, bytes;
+    int num_fix_blocks;  // tile engine: level-1 fix-up blocks
+    size_t off_coords, off_carry_rows, off_carry_vals, off_carry2_rows, off_carry2_vals, bytes;
     StreamGeom geom;    // stream engine only
 };
 
@@ -98,7 +91,7 @@ static int make_plan(int num_rows, int num_nonzeros, Plan<T>& p)
     DeviceInfo di;
     int rc = device_info(di);
     if (rc) return rc;
-    if (e == Engine::Auto) e = Engine::Stream;
+    if (e == Engine::Auto) e = Engine::Tile;
     p.engine = e;
     if (e == Engine::Stream) {
         p.geom = stream_geometry<T>(p.merge_items, di.sm_count);
@@ -113,6 +106,11 @@ static int make_plan(int num_rows, int num_nonzeros, Plan<T>& p)
     off += align256(sizeof(int) * (size_t)p.num_tiles);
     p.off_carry_vals = off;
     off += align256(sizeof(T) * (size_t)p.num_tiles);
+    p.num_fix_blocks = (p.num_tiles + TileCfg<T>::FIX - 1) / TileCfg<T>::FIX;
+    p.off_carry2_rows = off;
+    off += align256(sizeof(int) * (size_t)p.num_fix_blocks);
+    p.off_carry2_vals = off;
+    off += align256(sizeof(T) * (size_t)p.num_fix_blocks);
     p.bytes = off + 256;  // slack so an unaligned blob can be aligned up (util_device.cuh:68-80)
     return 0;
 }
@@ -146,24 +144,42 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
         rc = post_launch("spmv_stream_kernel", dim3(p.geom.num_swaths), dim3(p.geom.threads),
                          p.geom.smem_bytes, stream, debug_sync);
         if (rc) return rc;
-    } else {
-        using C = TileCfg<T>;
-        dim3 sgrid((p.num_tiles + 1 + 127) / 128), sblock(128);
-        tile_search_kernel<<<sgrid, sblock, 0, stream>>>(row_end, num_rows, num_nonzeros, C::TILE,
-                                                         p.num_tiles, coords);
-        int rc = post_launch("tile_search_kernel", sgrid, sblock, 0, stream, debug_sync);
-        if (rc) return rc;
-        dim3 grid(p.num_tiles), block(C::THREADS);
-        spmv_tile_kernel<T, C::THREADS, C::IPT, AXPBY><<<grid, block, 0, stream>>>(
-            values, row_end, col, x, y, num_rows, coords, carry_rows, carry_vals, alpha, beta);
-        rc = post_launch("spmv_tile_kernel", grid, block, 0, stream, debug_sync);
-        if (rc) return rc;
+        if (p.num_tiles > 1) {  // dispatch_spmv_orig.cuh:721
+            dim3 fgrid((p.num_tiles + 255) / 256), fblock(256);
+            carry_fixup_runs_kernel<T, AXPBY><<<fgrid, fblock, 0, stream>>>(carry_rows, carry_vals,
+                                                                           p.num_tiles, num_rows, y, alpha);
+            rc = post_launch("carry_fixup_runs_kernel", fgrid, fblock, 0, stream, debug_sync);
+            if (rc) return rc;
+        }
+        return 0;
     }
+
+    using C = TileCfg<T>;
+    int* carry2_rows = reinterpret_cast<int*>(temp + p.off_carry2_rows);
+    T* carry2_vals = reinterpret_cast<T*>(temp + p.off_carry2_vals);
+    dim3 sgrid((p.num_tiles + 1 + 127) / 128), sblock(128);
+    tile_search_kernel<<<sgrid, sblock, 0, stream>>>(row_end, num_rows, num_nonzeros, C::TILE, p.num_tiles,
+                                                     coords);
+    int rc = post_launch("tile_search_kernel", sgrid, sblock, 0, stream, debug_sync);
+    if (rc) return rc;
+    const int shift_v = (int)((reinterpret_cast<uintptr_t>(values) & 15) / sizeof(T));
+    const int shift_c = (int)((reinterpret_cast<uintptr_t>(col) & 15) / sizeof(int));
+    const int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
+    dim3 grid(p.num_tiles), block(C::THREADS);
+    spmv_tile_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
+                                                          carry_vals, alpha, beta, shift_v, shift_c, shift_r);
+    rc = post_launch("spmv_tile_kernel", grid, block, 0, stream, debug_sync);
+    if (rc) return rc;
     if (p.num_tiles > 1) {  // dispatch_spmv_orig.cuh:721
-        dim3 fgrid((p.num_tiles + 255) / 256), fblock(256);
-        carry_fixup_kernel<T, AXPBY><<<fgrid, fblock, 0, stream>>>(carry_rows, carry_vals, p.num_tiles,
-                                                                  num_rows, y, alpha);
-        int rc = post_launch("carry_fixup_kernel", fgrid, fblock, 0, stream, debug_sync);
+        dim3 fgrid(p.num_fix_blocks), fblock(C::FIX);
+        carry_fixup_block_kernel<T, AXPBY><<<fgrid, fblock, 0, stream>>>(
+            carry_rows, carry_vals, p.num_tiles, num_rows, y, alpha, carry2_rows, carry2_vals);
+        rc = post_launch("carry_fixup_block_kernel", fgrid, fblock, 0, stream, debug_sync);
+        if (rc) return rc;
+        dim3 f2grid((p.num_fix_blocks + 255) / 256), f2block(256);
+        carry_fixup_runs_kernel<T, AXPBY><<<f2grid, f2block, 0, stream>>>(carry2_rows, carry2_vals,
+                                                                         p.num_fix_blocks, num_rows, y, alpha);
+        rc = post_launch("carry_fixup_runs_kernel", f2grid, f2block, 0, stream, debug_sync);
         if (rc) return rc;
     }
     return 0;
@@ -535,7 +551,7 @@ int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out
             out[1] = TileCfg<T>::THREADS;
             out[2] = TileCfg<T>::TILE;
             out[3] = 0;
-            out[4] = p.num_tiles > 1 ? 3 : 2;
+            out[4] = p.num_tiles > 1 ? 4 : 2;
         }
         return 0;
     };

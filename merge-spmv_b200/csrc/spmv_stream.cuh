@@ -230,7 +230,7 @@ __device__ __forceinline__ int2 warp_merge_path_search_global(int64_t diag64,
 template <typename E>
 __device__ __forceinline__ uint32_t stage_range(const E* __restrict__ base, int shift, int lo, int hi,
                                                 E* ring, int mask, uint64_t* bar, uint64_t policy,
-                                                int lane)
+                                                int lane, int pos_base = 0)
 {
     constexpr int GRAN = 16 / (int)sizeof(E);
     if (lo >= hi) return 0;
@@ -247,54 +247,15 @@ __device__ __forceinline__ uint32_t stage_range(const E* __restrict__ base, int 
     int nhead = lo_al - lo, ntail = hi - hi_al;
     if (lane < nhead) {
         int i = lo + lane;
-        ring[(i + shift) & mask] = base[i];
+        ring[((i + shift) & mask) - pos_base] = base[i];
     } else if (lane >= 8 && lane - 8 < ntail) {
         int i = hi_al + (lane - 8);
-        ring[(i + shift) & mask] = base[i];
+        ring[((i + shift) & mask) - pos_base] = base[i];
     }
-    if (lane == 0 && bytes) bulk_g2s(ring + ((lo_al + shift) & mask), base + lo_al, bytes, bar, policy);
+    if (lane == 0 && bytes)
+        bulk_g2s(ring + (((lo_al + shift) & mask) - pos_base), base + lo_al, bytes, bar, policy);
     return bytes;
 }
-
-// ------------------------------------------------------------------------------------------------
-// Phase A helpers: products value * x[col] in place in the value ring
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-struct Vec4;
-template <>
-struct Vec4<float> {
-    float4 v;
-    __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
-    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
-    __device__ __forceinline__ void mul(float a, float b, float c, float d)
-    {
-        v.x *= a;
-        v.y *= b;
-        v.z *= c;
-        v.w *= d;
-    }
-};
-template <>
-struct Vec4<double> {
-    double2 lo, hi;
-    __device__ __forceinline__ void load(const double* p)
-    {
-        lo = *reinterpret_cast<const double2*>(p);
-        hi = *reinterpret_cast<const double2*>(p + 2);
-    }
-    __device__ __forceinline__ void store(double* p) const
-    {
-        *reinterpret_cast<double2*>(p) = lo;
-        *reinterpret_cast<double2*>(p + 2) = hi;
-    }
-    __device__ __forceinline__ void mul(double a, double b, double c, double d)
-    {
-        lo.x *= a;
-        lo.y *= b;
-        hi.x *= c;
-        hi.y *= d;
-    }
-};
 
 // ------------------------------------------------------------------------------------------------
 // The kernel.  VEC: values/column_indices bases are 16-byte aligned, so the gather stage works on

@@ -1,18 +1,48 @@
-// spmv_tile.cuh -- "tile" engine: one threadblock per fixed-size merge tile.
+// spmv_tile.cuh -- "tile" engine (default): one small threadblock per fixed-length diagonal swath
+// ("tile") of the (row_end_offsets (+) N_nnz) merge path, at full SM occupancy.
 //
-// This is the simple engine (selected with MSPMV_ENGINE=tile, and used for problems too small
-// for the persistent streaming engine in spmv_stream.cuh).  It keeps the reference's three-step
-// shape -- search kernel, tile kernel, carry fix-up kernel (dispatch_spmv_orig.cuh:665-745) --
-// but every step is re-written for sm_100a: plain LDG staging into shared memory, a per-thread
-// merge walk over smem products, a warp-shuffle segmented scan instead of BlockScan over
-// KeyValuePairs, and a deterministic (atomic-free) fix-up for both fp32 and fp64.
+// Shape of one CsrMV (the reference's launch sequence, dispatch_spmv_orig.cuh:665-745, re-built
+// for sm_100a):
+//   1. tile_search_kernel      MergePathSearch at every tile boundary (DeviceSpmvSearchKernel,
+//                              dispatch_spmv_orig.cuh:104-143) -> (row, nonzero) coordinates
+//   2. spmv_tile_kernel        128 threads x IPT merge items per block.  One warp stages the tile's
+//                              values / column indices / row offsets into shared memory with
+//                              cp.async.bulk (TMA, SASS UBLKCP) completing on an mbarrier -- copies
+//                              are 16-byte aligned for any tile start because the slice is taken
+//                              from the aligned-down address (ragged ends patched by scalar
+//                              copies).  Then: strip-mined LDG gather of x[col] and in-place
+//                              multiply (agent_spmv_orig.cuh:472-494); row ends scattered into a
+//                              bitmap (bit p <=> merge item p is a row end); every thread's start
+//                              coordinate is a popcount prefix of that bitmap -- the unique
+//                              coordinate the reference finds with a per-thread MergePathSearch
+//                              (agent_spmv_orig.cuh:539-545); branch-free unrolled walk over its
+//                              IPT flag bits (:557-578); warp-shuffle segmented scan closes rows
+//                              that span threads; finished rows go to y from registers; the
+//                              partial last row is the tile's carry-out (:906-913).
+//   3. carry_fixup_kernel(s)   deterministic two-level segmented reduction of the per-tile carries
+//                              into y (replaces DeviceSegmentFixupKernel,
+//                              dispatch_spmv_orig.cuh:199-224; no atomics, same result every run,
+//                              guard row < num_rows that the reference's GPU path lacks).
+// Latency (HBM stream, L2 gathers, shuffles) is hidden by thread-level parallelism: ~19 KB of
+// shared memory per block lets 10-16 blocks share an SM.
 #pragma once
 
 #include <limits.h>
 
 #include "merge_common.cuh"
+#include "spmv_stream.cuh"  // PTX wrappers (mbarrier, bulk copy) and stage_range()
 
 namespace mspmv {
+
+template <typename T>
+struct TileCfg {
+    static constexpr int THREADS = 128;
+    static constexpr int IPT = 9;                 // odd: the strided shared-memory walk is conflict-free for dense spans
+    static constexpr int TILE = THREADS * IPT;    // merge items per block
+    static constexpr int BW = TILE / 32 + 2;      // bitmap words
+    static constexpr int FIX = 256;               // carries per fix-up block
+    static_assert(TILE % 32 == 0 && (IPT & 1) == 1 && IPT < 32, "bitmap layout");
+};
 
 // ---- step 1: tile boundary coordinates (DeviceSpmvSearchKernel, dispatch_spmv_orig.cuh:104-143)
 __global__ void tile_search_kernel(const int* __restrict__ row_end_offsets, int num_rows,
@@ -35,82 +65,208 @@ __global__ void diagonal_search_kernel(const int* __restrict__ row_end_offsets, 
         coords[i] = merge_path_search_global(diagonals[i], row_end_offsets, num_rows, num_nonzeros);
 }
 
-// ---- step 2: one tile per threadblock (DeviceSpmvKernel / AgentSpmv::ConsumeTile,
-// dispatch_spmv_orig.cuh:158-186, agent_spmv_orig.cuh:413-639,856-914)
-template <typename T, int THREADS, int IPT, bool AXPBY>
-__global__ __launch_bounds__(THREADS) void spmv_tile_kernel(
-    const T* __restrict__ values, const int* __restrict__ row_end_offsets,
+// ---- step 2: one tile per threadblock
+template <typename T, bool AXPBY>
+__global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
+    const T* __restrict__ values, const int* __restrict__ row_offsets,
     const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
-    int num_rows, const int2* __restrict__ coords, int* __restrict__ carry_rows,
-    T* __restrict__ carry_vals, T alpha, T beta)
+    const int2* __restrict__ coords, int* __restrict__ carry_rows, T* __restrict__ carry_vals, T alpha,
+    T beta, int shift_v, int shift_c, int shift_r)
 {
-    constexpr int TILE = THREADS * IPT;
-    constexpr int NWARPS = THREADS / 32;
-    __shared__ int s_row_end[TILE + 1];
-    __shared__ T s_prod[TILE];
-    __shared__ T s_y[TILE];
-    __shared__ Seg<T> s_warp[NWARPS];
+    using C = TileCfg<T>;
+    constexpr int IPT = C::IPT;
+    constexpr int NW = C::THREADS / 32;
+    constexpr int GV = 16 / (int)sizeof(T);  // elements per 16 bytes
+    __shared__ alignas(128) T s_val[C::TILE + GV];
+    __shared__ alignas(128) int s_col[C::TILE + 4];
+    __shared__ alignas(128) int s_row[C::TILE + 4];
+    __shared__ alignas(16) uint32_t s_bits[C::BW];
+    __shared__ alignas(16) Seg<T> s_warp[NW];
+    __shared__ alignas(8) uint64_t s_bar;
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
-    const int2 c0 = coords[tile];
-    const int2 c1 = coords[tile + 1];
+    const int2 c0 = __ldg(coords + tile);
+    const int2 c1 = __ldg(coords + tile + 1);
     const int x0 = c0.x, y0 = c0.y;
-    const int nrows = c1.x - c0.x;
+    const int nrows = c1.x - c0.x;           // rows that end in this tile
     const int nnzs = c1.y - c0.y;
     const int items = nrows + nnzs;
 
-    // gather: products of the tile's nonzeros, strip-mined so loads coalesce
-    // (agent_spmv_orig.cuh:472-494)
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        int j = tid + i * THREADS;
-        if (j < nnzs) {
-            int c = __ldg(column_indices + y0 + j);
-            T v = __ldg(values + y0 + j);
-            s_prod[j] = v * __ldg(x + c);
+    // element i of an array lives at buffer position (i + shift) - base, base = aligned-down start
+    const int base_v = (y0 + shift_v) & ~(GV - 1);
+    const int base_c = (y0 + shift_c) & ~3;
+    const int jr0 = x0 + 1;                  // row_end_offsets[x0 + r] == row_offsets[jr0 + r]
+    const int base_r = (jr0 + shift_r) & ~3;
+    const int off_v = y0 + shift_v - base_v, off_c = y0 + shift_c - base_c, off_r = jr0 + shift_r - base_r;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < C::BW) s_bits[tid] = 0u;
+    __syncthreads();
+
+    // ---- TMA staging of the tile (warp 0) -----------------------------------------------------
+    if (warp == 0) {
+        const uint64_t policy = l2_policy_evict_first();
+        uint32_t b = stage_range<T>(values, shift_v, y0, y0 + nnzs, s_val, -1, &s_bar, policy, lane, base_v);
+        b += stage_range<int>(column_indices, shift_c, y0, y0 + nnzs, s_col, -1, &s_bar, policy, lane, base_c);
+        b += stage_range<int>(row_offsets, shift_r, jr0, jr0 + nrows, s_row, -1, &s_bar, policy, lane, base_r);
+        __syncwarp();
+        if (lane == 0) {
+            if (b) mbar_arrive_expect_tx(&s_bar, b);
+            else mbar_arrive(&s_bar);
         }
     }
-    // row-end offsets of the rows that end in this tile, plus a sentinel instead of the
-    // reference's tile_num_rows+1'th load (agent_spmv_orig.cuh:527-531)
-    for (int j = tid; j < nrows; j += THREADS) s_row_end[j] = __ldg(row_end_offsets + x0 + j);
-    if (tid == 0) s_row_end[nrows] = INT_MAX;
+    mbar_wait(&s_bar, 0);
+
+    // ---- gather x[col] and multiply in place, strip-mined so the index stream is coalesced -----
+    {
+        int cidx[IPT];
+        T xv[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const int j = tid + i * C::THREADS;
+            cidx[i] = j < nnzs ? s_col[off_c + j] : -1;
+        }
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? __ldg(x + cidx[i]) : T(0);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const int j = tid + i * C::THREADS;
+            if (j < nnzs) s_val[off_v + j] *= xv[i];
+        }
+    }
+    // ---- row-end flags: merge item p = row_end[r] - y0 + r is the end of local row r ------------
+    for (int r = tid; r < nrows; r += C::THREADS) {
+        const int pos = s_row[off_r + r] - y0 + r;
+        atomicOr(&s_bits[pos >> 5], 1u << (pos & 31));
+    }
     __syncthreads();
 
-    Seg<T> elem;
-    int head_row;
-    T head_val;
-    thread_merge_walk<T, IPT>(
-        tid * IPT, items, nrows, nnzs, y0, [&](int i) { return s_row_end[i]; },
-        [&](int j) { return s_prod[j]; }, [&](int r, T v) { s_y[r] = v; }, elem, head_row, head_val);
+    // ---- my IPT flag bits; row ends before my first item == my start row (popcount prefix) ------
+    const int diag = tid * IPT;
+    const uint32_t w0 = s_bits[diag >> 5], w1 = s_bits[(diag >> 5) + 1];
+    const uint32_t bits = __funnelshift_r(w0, w1, diag & 31) & ((1u << IPT) - 1u);
+    int before_warp = 0;
+#pragma unroll
+    for (int k = lane; k < NW * IPT; k += 32)
+        if (k < warp * IPT) before_warp += __popc(s_bits[k]);  // warp w owns words [w*IPT, (w+1)*IPT)
+    before_warp = __reduce_add_sync(kFull, before_warp);
+    int in_warp = __popc(w0 & ((1u << (diag & 31)) - 1u));
+#pragma unroll
+    for (int k = 0; k < IPT - 1; ++k)
+        if (warp * IPT + k < (diag >> 5)) in_warp += __popc(s_bits[warp * IPT + k]);
+    const int xs = before_warp + in_warp;
 
-    Seg<T> zero;
+    // ---- serial walk over my IPT merge items (cpu_spmv.cpp:324-340; agent_spmv_orig.cuh:557-578)
+    const int my_items = min(max(items - diag, 0), IPT);
+    int ny = off_v + diag - xs;              // buffer position of my first product
+    T sums[IPT];
+    T running = T(0);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const bool is_end = (bits >> i) & 1u;
+        if (!is_end && i < my_items) running += s_val[ny];
+        ny += is_end ? 0 : 1;
+        sums[i] = running;
+        if (is_end) running = T(0);
+    }
+    Seg<T> elem, zero, excl, total;
+    elem.val = running;
+    elem.ended = bits != 0u;
     zero.val = T(0);
     zero.ended = 0;
-    Seg<T> excl, total;
-    block_seg_scan_exclusive<T, NWARPS>(elem, zero, s_warp, tid, 1, excl, total);
-    if (elem.ended) s_y[head_row] = head_val + excl.val;
-    __syncthreads();
+    block_seg_scan_exclusive<T, NW>(elem, zero, s_warp, tid, 1, excl, total);
 
-    for (int j = tid; j < nrows; j += THREADS)
-        y[x0 + j] = epilogue<T, AXPBY>(s_y[j], alpha, beta, y + x0 + j);
-
-    // carry-out: partial sum of the row that continues into the next tile
-    // (agent_spmv_orig.cuh:906-913).  Row index c1.x may equal num_rows; the fix-up drops it.
+    // ---- finished rows to y from registers; my first row end also takes the carry-in -------------
+    {
+        int row = x0 + xs;
+        T add = excl.val;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            if ((bits >> i) & 1u) {
+                y[row] = epilogue<T, AXPBY>(sums[i] + add, alpha, beta, y + row);
+                add = T(0);
+                ++row;
+            }
+        }
+    }
+    // carry-out: the row that continues into the next tile (agent_spmv_orig.cuh:906-913).
+    // c1.x may equal num_rows; the fix-up drops such carries.
     if (tid == 0) {
         carry_rows[tile] = c1.x;
         carry_vals[tile] = total.val;
     }
 }
 
-// ---- step 3: deterministic carry fix-up (replaces DeviceSegmentFixupKernel,
-// dispatch_spmv_orig.cuh:199-224 / agent_segment_fixup.cuh:226-341).  The n carries are sorted
-// by row.  The thread owning the first carry of each row sums that row's run left to right
-// and adds it to y once: same order as the CPU loop cpu_spmv.cpp:348-352, no atomics, and the
-// guard row < num_rows that the reference's GPU path lacks.
+// ---- step 3: deterministic carry fix-up -------------------------------------------------------
+// Level 1: blocks of FIX consecutive carries (sorted by row).  Within a block, runs of equal rows
+// are summed left to right; a run that ends inside the block is added to y once; the run that
+// touches the end of the block is handed to level 2 as (row, partial).
 template <typename T, bool AXPBY>
-__global__ void carry_fixup_kernel(const int* __restrict__ carry_rows, const T* __restrict__ carry_vals,
-                                   int n, int num_rows, T* __restrict__ y, T alpha)
+__global__ __launch_bounds__(256) void carry_fixup_block_kernel(const int* __restrict__ carry_rows,
+                                                                const T* __restrict__ carry_vals, int n,
+                                                          int num_rows, T* __restrict__ y, T alpha,
+                                                          int* __restrict__ carry2_rows,
+                                                          T* __restrict__ carry2_vals)
+{
+    constexpr int FIX = 256;
+    __shared__ Seg<T> s_warp[FIX / 32];
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * FIX + tid;
+    const int row = i < n ? carry_rows[i] : INT_MAX;
+    const T val = i < n ? carry_vals[i] : T(0);
+    const int prev_row = (i > 0 && tid > 0) ? carry_rows[i - 1] : -1;  // block-local run detection
+    const int next_row = (i + 1 < n) ? carry_rows[i + 1] : INT_MAX;
+
+    // inclusive segmented scan keyed by "row differs from the previous carry in this block"
+    Seg<T> e;
+    e.val = val;
+    e.ended = (tid == 0) || (row != prev_row);  // a new run starts here
+    // scan with "run start" flags: value accumulates since the most recent start
+    const int lane = tid & 31, warp = tid >> 5;
+    Seg<T> inc = e;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T v = shfl_up(inc.val, d);
+        int f = __shfl_up_sync(kFull, inc.ended, d);
+        if (lane >= d) {
+            if (!inc.ended) inc.val += v;
+            inc.ended |= f;
+        }
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    Seg<T> run;
+    run.val = T(0);
+    run.ended = 1;
+    for (int w = 0; w < warp; ++w) {
+        Seg<T> t = s_warp[w];
+        run.val = t.ended ? t.val : run.val + t.val;
+    }
+    const T run_sum = inc.ended ? inc.val : run.val + inc.val;  // sum of my run up to and including me
+
+    const bool last_in_block = (tid == FIX - 1) || (i == n - 1);
+    if (i < n) {
+        if (last_in_block) {
+            carry2_rows[blockIdx.x] = row;
+            carry2_vals[blockIdx.x] = run_sum;
+        } else if (row != next_row && row < num_rows) {
+            y[row] += AXPBY ? alpha * run_sum : run_sum;
+        }
+    }
+}
+
+// Level 2 (and the stream engine's only level): the n carries are sorted by row; the thread that
+// owns the first carry of a run sums the run left to right and adds it to y once -- the order of
+// the CPU loop cpu_spmv.cpp:348-352.  Runs here are short (a row must span > FIX tiles to put two
+// entries in one run).
+template <typename T, bool AXPBY>
+__global__ void carry_fixup_runs_kernel(const int* __restrict__ carry_rows, const T* __restrict__ carry_vals,
+                                        int n, int num_rows, T* __restrict__ y, T alpha)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -119,8 +275,7 @@ __global__ void carry_fixup_kernel(const int* __restrict__ carry_rows, const T* 
     if (i > 0 && carry_rows[i - 1] == row) return;  // not the head of this row's run
     T sum = carry_vals[i];
     for (int j = i + 1; j < n && carry_rows[j] == row; ++j) sum += carry_vals[j];
-    if (AXPBY) sum *= alpha;
-    y[row] += sum;
+    y[row] += AXPBY ? alpha * sum : sum;
 }
 
 }  // namespace mspmv

@@ -275,11 +275,12 @@ def test_alpha_beta(orc, engine, dt):
         assert np.all(np.abs(got - want) <= tol), (alpha, beta)
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
-def test_misaligned_base_pointers(dt):
+def test_misaligned_base_pointers(engine, dt):
     """Sub-array views whose bases are not 16-byte aligned (shards, user slices) take the same
     TMA path with ragged edges patched."""
-    set_engine("stream")
+    set_engine(engine)
     m = gen.make_config("powerlaw_2m", scale=1 / 64, dtype=dt, values="random")
     x = gen.vector(m.cols, dt, "random").to(DEV)
     base = ms.csrmv(*(t.to(DEV) for t in (m.row_offsets, m.col, m.val)), x).clone()
