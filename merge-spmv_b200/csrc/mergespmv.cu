@@ -167,7 +167,8 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     const int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
     dim3 grid(p.num_tiles), block(C::THREADS);
     spmv_tile_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
-                                                          carry_vals, alpha, beta, shift_v, shift_c, shift_r);
+                                                          carry_vals, alpha, beta, num_rows, num_nonzeros, shift_v,
+                                                          shift_c, shift_r);
     rc = post_launch("spmv_tile_kernel", grid, block, 0, stream, debug_sync);
     if (rc) return rc;
     if (p.num_tiles > 1) {  // dispatch_spmv_orig.cuh:721

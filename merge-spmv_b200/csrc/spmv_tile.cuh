@@ -41,6 +41,7 @@ struct TileCfg {
     static constexpr int TILE = THREADS * IPT;    // merge items per block
     static constexpr int BW = TILE / 32 + 2;      // bitmap words
     static constexpr int FIX = 256;               // carries per fix-up block
+    static constexpr int ROWCAP = 384;            // row offsets staged in shared memory; tiles with more read them from L2
     static_assert(TILE % 32 == 0 && (IPT & 1) == 1 && IPT < 32, "bitmap layout");
 };
 
@@ -71,15 +72,15 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     const T* __restrict__ values, const int* __restrict__ row_offsets,
     const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
     const int2* __restrict__ coords, int* __restrict__ carry_rows, T* __restrict__ carry_vals, T alpha,
-    T beta, int shift_v, int shift_c, int shift_r)
+    T beta, int num_rows, int num_nonzeros, int shift_v, int shift_c, int shift_r)
 {
     using C = TileCfg<T>;
     constexpr int IPT = C::IPT;
     constexpr int NW = C::THREADS / 32;
     constexpr int GV = 16 / (int)sizeof(T);  // elements per 16 bytes
-    __shared__ alignas(128) T s_val[C::TILE + GV];
-    __shared__ alignas(128) int s_col[C::TILE + 4];
-    __shared__ alignas(128) int s_row[C::TILE + 4];
+    __shared__ alignas(128) T s_val[C::TILE + 2 * GV];
+    __shared__ alignas(128) int s_col[C::TILE + 8];
+    __shared__ alignas(128) int s_row[C::ROWCAP + 8];
     __shared__ alignas(16) uint32_t s_bits[C::BW];
     __shared__ alignas(16) Seg<T> s_warp[NW];
     __shared__ alignas(8) uint64_t s_bar;
@@ -111,9 +112,13 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     // ---- TMA staging of the tile (warp 0) -----------------------------------------------------
     if (warp == 0) {
         const uint64_t policy = l2_policy_evict_first();
-        uint32_t b = stage_range<T>(values, shift_v, y0, y0 + nnzs, s_val, -1, &s_bar, policy, lane, base_v);
-        b += stage_range<int>(column_indices, shift_c, y0, y0 + nnzs, s_col, -1, &s_bar, policy, lane, base_c);
-        b += stage_range<int>(row_offsets, shift_r, jr0, jr0 + nrows, s_row, -1, &s_bar, policy, lane, base_r);
+        uint32_t b = stage_superset<T>(values, shift_v, y0, y0 + nnzs, num_nonzeros, s_val, base_v, &s_bar,
+                                       policy, lane);
+        b += stage_superset<int>(column_indices, shift_c, y0, y0 + nnzs, num_nonzeros, s_col, base_c, &s_bar,
+                                 policy, lane);
+        if (nrows <= C::ROWCAP)
+            b += stage_superset<int>(row_offsets, shift_r, jr0, jr0 + nrows, num_rows + 1, s_row, base_r,
+                                     &s_bar, policy, lane);
         __syncwarp();
         if (lane == 0) {
             if (b) mbar_arrive_expect_tx(&s_bar, b);
@@ -141,7 +146,8 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     }
     // ---- row-end flags: merge item p = row_end[r] - y0 + r is the end of local row r ------------
     for (int r = tid; r < nrows; r += C::THREADS) {
-        const int pos = s_row[off_r + r] - y0 + r;
+        const int e = nrows <= C::ROWCAP ? s_row[off_r + r] : __ldg(row_offsets + jr0 + r);
+        const int pos = e - y0 + r;
         atomicOr(&s_bits[pos >> 5], 1u << (pos & 31));
     }
     __syncthreads();
