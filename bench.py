@@ -329,9 +329,9 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(f"{name}@{world}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_stream_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tile_kernel" if (args.engine or "tile") != "stream" else "spmv_stream_kernel",
                 "algorithmic_bytes_per_launch": shard_bytes,
-                "note": "duration = whole step (stream kernel + carry fix-up kernel), CUDA events"}
+                "note": "duration = whole step (search + spmv + carry fix-up kernels), CUDA events"}
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------
     e2e = None
@@ -399,7 +399,7 @@ def main():
                        "columns": "banded" if kind == "banded" else "stratified-uniform, sorted, distinct",
                        "parallelism": f"merge-path shards x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
-                       "engine": args.engine or "stream"},
+                       "engine": args.engine or "tile"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "hbm_gbs_algorithmic": achieved * (1 if world == 1 else world),

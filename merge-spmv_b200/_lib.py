@@ -40,7 +40,8 @@ class MergeSpmvError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libmergespmv.so")
+    # MSPMV_LIB picks an alternative build of the same library (tuning experiments only)
+    return os.environ.get("MSPMV_LIB") or os.path.join(_HERE, "libmergespmv.so")
 
 
 _lib = None

@@ -166,6 +166,21 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     const int shift_c = (int)((reinterpret_cast<uintptr_t>(col) & 15) / sizeof(int));
     const int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
     dim3 grid(p.num_tiles), block(C::THREADS);
+    {
+        // Shared-memory carve-out: the x gathers need L1 capacity for their misses in flight
+        // (gather throughput halves once shared memory takes > ~160 KB of the 228 KB, see
+        // profiles/microbench_r01.txt), so cap what the resident blocks may claim.
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
+            int pct = 70;  // ~160 KB shared, ~68 KB L1 (the driver default for this footprint; pinned so larger tiles keep it)
+            if (const char* e = std::getenv("MSPMV_TILE_CARVEOUT")) pct = std::atoi(e);
+            if (pct >= 0)
+                cudaFuncSetAttribute(spmv_tile_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            configured[dev & 63] = true;
+        }
+    }
     spmv_tile_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
                                                           carry_vals, alpha, beta, num_rows, num_nonzeros, shift_v,
                                                           shift_c, shift_r);

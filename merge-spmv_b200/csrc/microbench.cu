@@ -159,6 +159,36 @@ __global__ void gather_kernel(const int* __restrict__ idx, const T* __restrict__
     if (acc == T(-12345)) out[0] = acc;
 }
 
+// gather flavours vs. L1 capacity: MODE 0 = ld.global.nc, 1 = ld.global.cg, 2 = ld.global.nc.L1::no_allocate,
+// 3 = ld.global.cv (volatile)
+template <int MODE>
+__device__ __forceinline__ double ld_flavour(const double* p)
+{
+    double v;
+    if (MODE == 0) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    if (MODE == 1) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    if (MODE == 2) asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    if (MODE == 3) asm volatile("ld.global.cv.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <int MODE, int U>
+__global__ void gather_flavour_kernel(const int* __restrict__ idx, const double* __restrict__ table, size_t n,
+                                      double* out)
+{
+    extern __shared__ unsigned char pad[];
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    double acc = 0;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        int c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) c[u] = __ldcs(idx + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += ld_flavour<MODE>(table + c[u]);
+    }
+    if (acc == -12345.0) out[0] = acc + pad[threadIdx.x];
+}
+
 template <typename F>
 static float time_ms(F launch, int iters = 5)
 {
@@ -265,6 +295,34 @@ int main()
         }
     }
     CK(cudaFree(buf));
+    {   // gather flavour x shared-memory carve-out (L1 capacity) experiment
+        const size_t n = 64ull << 20;
+        int* idx;
+        double *table, *out;
+        CK(cudaMalloc(&idx, n * sizeof(int)));
+        CK(cudaMalloc(&table, (1 << 20) * sizeof(double)));
+        CK(cudaMalloc(&out, 64));
+        fill_vals<double><<<(1 << 20) / 256, 256>>>(table, 1 << 20, 3);
+        fill_indices<<<(unsigned)((n + 255) / 256), 256>>>(idx, n, 1 << 20, 64, 0, 11);
+        CK(cudaDeviceSynchronize());
+        const int smem_per_block[] = {0, 8 << 10, 16 << 10, 20 << 10, 24 << 10, 27 << 10};
+        auto run = [&](auto kern, const char* name) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 27 << 10));
+            for (int sb : smem_per_block) {
+                float ms = time_ms([&] { kern<<<sms * 8, 256, sb>>>(idx, table, n, out); });
+                std::printf("gather_flavour %s smem/SM=%3d KB: %.3f ms  %.1f Ggather/s\n", name, sb * 8 >> 10, ms,
+                            n / ms / 1e6);
+            }
+        };
+        run(gather_flavour_kernel<0, 8>, "ld.global.nc      ");
+        run(gather_flavour_kernel<1, 8>, "ld.global.cg      ");
+        run(gather_flavour_kernel<2, 8>, "ld.nc.no_allocate ");
+        run(gather_flavour_kernel<3, 8>, "ld.global.cv      ");
+        CK(cudaFree(idx));
+        CK(cudaFree(table));
+        CK(cudaFree(out));
+    }
+    if (std::getenv("MICROBENCH_FLAVOURS_ONLY")) return 0;
     gather_suite<double>("f64", sms);
     gather_suite<float>("f32", sms);
     std::printf("microbench done\n");

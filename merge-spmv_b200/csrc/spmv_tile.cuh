@@ -36,8 +36,17 @@ namespace mspmv {
 
 template <typename T>
 struct TileCfg {
-    static constexpr int THREADS = 128;
-    static constexpr int IPT = 9;                 // odd: the strided shared-memory walk is conflict-free for dense spans
+#ifndef MSPMV_TILE_THREADS
+#define MSPMV_TILE_THREADS 128
+#endif
+    // Merge items per thread, tuned on B200 (profiles/tuning_r01.txt): fp64 9, fp32 13 -- both give
+    // ~15 KB of shared memory per block.  Odd, so the strided shared-memory walk is conflict-free
+    // for dense spans.
+#ifndef MSPMV_TILE_IPT
+#define MSPMV_TILE_IPT (sizeof(T) == 8 ? 9 : 13)
+#endif
+    static constexpr int THREADS = MSPMV_TILE_THREADS;
+    static constexpr int IPT = MSPMV_TILE_IPT;
     static constexpr int TILE = THREADS * IPT;    // merge items per block
     static constexpr int BW = TILE / 32 + 2;      // bitmap words
     static constexpr int FIX = 256;               // carries per fix-up block
@@ -64,6 +73,32 @@ __global__ void diagonal_search_kernel(const int* __restrict__ row_end_offsets, 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
         coords[i] = merge_path_search_global(diagonals[i], row_end_offsets, num_rows, num_nonzeros);
+}
+
+// x gather: read-only path, do not keep the line in L1 after use (random gathers have no reuse and
+// L1 capacity is what bounds the number of misses in flight -- profiles/microbench_r01.txt)
+#ifndef MSPMV_GATHER_FLAVOUR
+#define MSPMV_GATHER_FLAVOUR 2
+#endif
+__device__ __forceinline__ float ld_gather(const float* p)
+{
+#if MSPMV_GATHER_FLAVOUR == 2
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double ld_gather(const double* p)
+{
+#if MSPMV_GATHER_FLAVOUR == 2
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
 }
 
 // ---- step 2: one tile per threadblock
@@ -137,7 +172,7 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
             cidx[i] = j < nnzs ? s_col[off_c + j] : -1;
         }
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? __ldg(x + cidx[i]) : T(0);
+        for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? ld_gather(x + cidx[i]) : T(0);
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const int j = tid + i * C::THREADS;
