@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--engine", default=None, choices=[None, "stream", "tile", "auto"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay each step as one CUDA graph (auto: on for N>1, where the collective's host cost matters)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -282,9 +284,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
+    c0 = L.mspmv_launch_count()
+    op(x)  # one eager step: also counts this library's kernels per step (graph replays bypass the counter)
+    launches_per_step = L.mspmv_launch_count() - c0
+    step = op.capture(x) if use_graph else (lambda: op(x))
+
     # ---- warm-up + correctness guard (exact identity on ones; finite on random) ----------------
     for _ in range(args.warmup):
-        y = op(x)
+        y = step()
     torch.cuda.synchronize()
     if args.values == "ones":
         lens = torch.diff(torch.from_numpy(ro_np[shard.x0: shard.x1 + 1])).to(dt).to(dev)
@@ -300,10 +308,12 @@ def main():
     with sampler:
         start.record()
         for _ in range(args.steps):
-            op(x)
+            step()
         stop.record()
         stop.synchronize()
     launches = L.mspmv_launch_count() - launches0
+    if use_graph:
+        launches = launches_per_step * args.steps  # replayed from the captured graph
     barrier()
     elapsed_ms = start.elapsed_time(stop)
     if world > 1:
@@ -399,7 +409,7 @@ def main():
                        "columns": "banded" if kind == "banded" else "stratified-uniform, sorted, distinct",
                        "parallelism": f"merge-path shards x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
-                       "engine": args.engine or "tile"},
+                       "engine": args.engine or "tile", "cuda_graph": use_graph},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "hbm_gbs_algorithmic": achieved * (1 if world == 1 else world),
@@ -408,6 +418,14 @@ def main():
             line["config"]["powerlaw_alpha"] = alpha
         print(json.dumps(line), flush=True)
     if world > 1:
+        # A captured graph holds NCCL work; tearing the communicator down under it can hang, so
+        # release the graph first and leave without the (optional) collective teardown.
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        step = None
+        if use_graph:
+            os._exit(0)
         dist.destroy_process_group()
     return 0
 

@@ -1,0 +1,67 @@
+"""N>1 on real GPUs: one process per GPU over NCCL (skipped on boxes with a single GPU; the host
+logic of the same path is covered on CPU by tests/test_sharded_gloo.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, dtype_name, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import oracle
+    import merge_spmv_b200 as ms
+    from merge_spmv_b200 import generators as gen
+    from merge_spmv_b200 import sharded
+
+    dt = getattr(torch, dtype_name)
+    m = gen.make_config("powerlaw_2m", scale=1 / 32, dtype=dt, values="random")
+    ro, col, val = m.numpy()
+    x = gen.vector(m.cols, dt, "random", device=dev)
+    md = m.to(dev)
+    shard = sharded.make_shard(ro, m.cols, rank, world, lambda k0, k1: (md.col[k0:k1], md.val[k0:k1]), dev)
+    op = sharded.ShardedSpmv(shard)
+    for _ in range(3):
+        y_own = op(x)
+    torch.cuda.synchronize()
+    full = ms.csrmv(md.row_offsets, md.col, md.val, x)
+    ok_local = torch.allclose(y_own, full[shard.x0:shard.x1], rtol=1e-5 if dt == torch.float32 else 1e-12, atol=0)
+    want = oracle.Oracle().merge_csrmv(ro, col, val, x.cpu().numpy(), world)[shard.x0:shard.x1]
+    got = y_own.cpu().numpy()
+    lens = np.diff(ro)[shard.x0:shard.x1].astype(np.float64)
+    tol = 1e-10 if dt == torch.float64 else np.maximum(1e-6, 4 * np.sqrt(lens) * 2.0 ** -24)
+    ok_oracle = bool(np.all(np.abs(got - want) <= tol * np.abs(want)))
+    flag = torch.tensor([int(ok_local and ok_oracle)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.save(os.path.join(out_dir, f"ok_{dtype_name}.npy"), np.array([int(flag.item())]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype_name", ["float64", "float32"])
+def test_sharded_spmv_nccl(tmp_path, dtype_name):
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(world, 8)
+    mp.spawn(_worker, args=(world, _free_port(), dtype_name, str(tmp_path)), nprocs=world, join=True)
+    assert np.load(tmp_path / f"ok_{dtype_name}.npy")[0] == 1
