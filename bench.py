@@ -48,8 +48,11 @@ def workload_spec(name, n_gpus):
     p = dict(p)
     scaling = "weak"
     if name == "uniform_1m_64" and n_gpus > 1:
+        # weak scaling: every GPU gets a config-2-sized shard (2^20 rows x 2^20 columns, 64 nnz/row) of
+        # an (N * 2^20) x 2^20 matrix, so x -- replicated on every GPU -- keeps its N=1 size and the
+        # per-GPU work is exactly the N=1 work.  (Growing the columns with N as well measures L2
+        # capacity for x, not the path: see DESIGN.md section 6.)
         p["rows"] *= n_gpus
-        p["cols"] *= n_gpus
     elif n_gpus > 1:
         scaling = "strong"
     return name, kind, dt, p, scaling
@@ -234,6 +237,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--engine", default=None, choices=[None, "stream", "tile", "auto"])
+    ap.add_argument("--cols", type=int, default=None, help="override the column count (x length) of the workload")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay each step as one CUDA graph (auto: on for N>1, where the collective's host cost matters)")
     args = ap.parse_args()
@@ -267,6 +271,8 @@ def main():
         ms.lib().mspmv_set_engine(args.engine.encode())
 
     name, kind, dt, p, scaling = workload_spec(args.workload, world)
+    if args.cols:
+        p["cols"] = args.cols
     vb = 8 if dt == torch.float64 else 4
     ro, cols, alpha = build_row_offsets(kind, p)
     rows, nnz = ro.numel() - 1, int(ro[-1])

@@ -75,11 +75,32 @@ __global__ void diagonal_search_kernel(const int* __restrict__ row_end_offsets, 
         coords[i] = merge_path_search_global(diagonals[i], row_end_offsets, num_rows, num_nonzeros);
 }
 
-// x gather: read-only path, do not keep the line in L1 after use (random gathers have no reuse and
-// L1 capacity is what bounds the number of misses in flight -- profiles/microbench_r01.txt)
+// x gather: read-only path; do not keep the line in L1 after use (random gathers have no reuse and
+// L1 capacity is what bounds the number of misses in flight -- profiles/microbench_r01.txt); and
+// mark it L2::evict_last while the value / index / row-offset streams are L2::evict_first, so x --
+// the only reused data -- stays L2-resident even when it is tens of MB (profiles/tuning_r01.txt:
+// 20M-column power-law 12.98 -> 5.78 ms).  Flavours: 0 = __ldg, 2 = no_allocate, 3 = + evict_last.
 #ifndef MSPMV_GATHER_FLAVOUR
-#define MSPMV_GATHER_FLAVOUR 2
+#define MSPMV_GATHER_FLAVOUR 3
 #endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float ld_gather(const float* p, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_gather(const double* p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ float ld_gather(const float* p)
 {
 #if MSPMV_GATHER_FLAVOUR == 2
@@ -171,8 +192,14 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
             const int j = tid + i * C::THREADS;
             cidx[i] = j < nnzs ? s_col[off_c + j] : -1;
         }
+#if MSPMV_GATHER_FLAVOUR == 3
+        const uint64_t keep = l2_policy_evict_last();  // x is the only reused data: keep it in L2
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? ld_gather(x + cidx[i], keep) : T(0);
+#else
 #pragma unroll
         for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? ld_gather(x + cidx[i]) : T(0);
+#endif
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const int j = tid + i * C::THREADS;

@@ -71,6 +71,13 @@ def uniform_row_offsets(rows, nnz_per_row):
     return (torch.arange(rows + 1, dtype=torch.int64) * nnz_per_row).to(torch.int32)
 
 
+# bisection results for the two BASELINE.json power-law configs (saves 60 passes over 2-20 M rows)
+_KNOWN_ALPHA = {
+    (2_000_000, 1_000_000, 200_000_000): 0.7215631890166361,
+    (20_000_000, 1_000_000, 1_000_000_000): 0.6509830663579996,
+}
+
+
 def powerlaw_row_lengths(rows, max_row, target_nnz, seed=0x5EED0003):
     """len(k) = max(1, floor(max_row / k^alpha)), k = 1..rows, alpha solved so the sum hits
     target_nnz; rank -> row by a seeded permutation.  Returns (lengths int64[rows], alpha)."""
@@ -79,14 +86,16 @@ def powerlaw_row_lengths(rows, max_row, target_nnz, seed=0x5EED0003):
     def total(alpha):
         return int(torch.clamp(torch.floor(max_row / torch.pow(k, alpha)), min=1).sum().item())
 
-    lo, hi = 0.0, 4.0
-    for _ in range(60):
-        mid = 0.5 * (lo + hi)
-        if total(mid) > target_nnz:
-            lo = mid
-        else:
-            hi = mid
-    alpha = hi
+    alpha = _KNOWN_ALPHA.get((rows, max_row, target_nnz))
+    if alpha is None:
+        lo, hi = 0.0, 4.0
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            if total(mid) > target_nnz:
+                lo = mid
+            else:
+                hi = mid
+        alpha = hi
     lengths = torch.clamp(torch.floor(max_row / torch.pow(k, alpha)), min=1).to(torch.int64)
     perm = torch.argsort(splitmix64(torch.arange(rows, dtype=torch.int64) + _s64(seed)))
     out = torch.empty_like(lengths)
