@@ -79,7 +79,7 @@ struct Plan {
     int64_t merge_items;
     int num_tiles;      // tile engine: tiles; stream engine: swaths (threadblocks)
     int num_fix_blocks;  // tile engine: level-1 fix-up blocks
-    size_t off_coords, off_carry_rows, off_carry_vals, off_carry2_rows, off_carry2_vals, bytes;
+    size_t off_coords, off_carry_rows, off_carry_vals, off_carry2_rows, off_carry2_vals, off_ticket, bytes;
     StreamGeom geom;    // stream engine only
 };
 
@@ -111,6 +111,8 @@ static int make_plan(int num_rows, int num_nonzeros, Plan<T>& p)
     off += align256(sizeof(int) * (size_t)p.num_fix_blocks);
     p.off_carry2_vals = off;
     off += align256(sizeof(T) * (size_t)p.num_fix_blocks);
+    p.off_ticket = off;
+    off += 256;
     p.bytes = off + 256;  // slack so an unaligned blob can be aligned up (util_device.cuh:68-80)
     return 0;
 }
@@ -157,9 +159,10 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     using C = TileCfg<T>;
     int* carry2_rows = reinterpret_cast<int*>(temp + p.off_carry2_rows);
     T* carry2_vals = reinterpret_cast<T*>(temp + p.off_carry2_vals);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(temp + p.off_ticket);
     dim3 sgrid((p.num_tiles + 1 + 127) / 128), sblock(128);
     tile_search_kernel<<<sgrid, sblock, 0, stream>>>(row_end, num_rows, num_nonzeros, C::TILE, p.num_tiles,
-                                                     coords);
+                                                     coords, ticket);
     int rc = post_launch("tile_search_kernel", sgrid, sblock, 0, stream, debug_sync);
     if (rc) return rc;
     const int shift_v = (int)((reinterpret_cast<uintptr_t>(values) & 15) / sizeof(T));
@@ -189,13 +192,8 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     if (p.num_tiles > 1) {  // dispatch_spmv_orig.cuh:721
         dim3 fgrid(p.num_fix_blocks), fblock(C::FIX);
         carry_fixup_block_kernel<T, AXPBY><<<fgrid, fblock, 0, stream>>>(
-            carry_rows, carry_vals, p.num_tiles, num_rows, y, alpha, carry2_rows, carry2_vals);
+            carry_rows, carry_vals, p.num_tiles, num_rows, y, alpha, carry2_rows, carry2_vals, ticket);
         rc = post_launch("carry_fixup_block_kernel", fgrid, fblock, 0, stream, debug_sync);
-        if (rc) return rc;
-        dim3 f2grid((p.num_fix_blocks + 255) / 256), f2block(256);
-        carry_fixup_runs_kernel<T, AXPBY><<<f2grid, f2block, 0, stream>>>(carry2_rows, carry2_vals,
-                                                                         p.num_fix_blocks, num_rows, y, alpha);
-        rc = post_launch("carry_fixup_runs_kernel", f2grid, f2block, 0, stream, debug_sync);
         if (rc) return rc;
     }
     return 0;
@@ -359,7 +357,7 @@ int mspmv_csrmv_swath_coords(const int* d_row_offsets, int num_rows, int num_non
     if (!d_coords) return 0;
     dim3 grid((n + 1 + 127) / 128), block(128);
     tile_search_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-        d_row_offsets + 1, num_rows, num_nonzeros, (int)per, n, reinterpret_cast<int2*>(d_coords));
+        d_row_offsets + 1, num_rows, num_nonzeros, (int)per, n, reinterpret_cast<int2*>(d_coords), nullptr);
     return post_launch("tile_search_kernel", grid, block, 0, (cudaStream_t)stream, 0);
 }
 
@@ -567,7 +565,7 @@ int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out
             out[1] = TileCfg<T>::THREADS;
             out[2] = TileCfg<T>::TILE;
             out[3] = 0;
-            out[4] = p.num_tiles > 1 ? 4 : 2;
+            out[4] = p.num_tiles > 1 ? 3 : 2;
         }
         return 0;
     };

@@ -55,11 +55,15 @@ struct TileCfg {
 };
 
 // ---- step 1: tile boundary coordinates (DeviceSpmvSearchKernel, dispatch_spmv_orig.cuh:104-143)
+// One thread per boundary (a 32-ary warp-cooperative variant was measured slower here: 18.9 vs
+// 10.7 us for 59k boundaries -- it turns a latency-bound kernel into a load-throughput-bound one).
+// Also clears the fix-up ticket counter for this call (the temp blob arrives uninitialised).
 __global__ void tile_search_kernel(const int* __restrict__ row_end_offsets, int num_rows,
                                    int num_nonzeros, int tile_items, int num_tiles,
-                                   int2* __restrict__ coords)
+                                   int2* __restrict__ coords, unsigned int* __restrict__ ticket)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ticket != nullptr && i == 0) *ticket = 0u;
     if (i <= num_tiles)
         coords[i] = merge_path_search_global((int64_t)i * tile_items, row_end_offsets, num_rows,
                                              num_nonzeros);
@@ -203,7 +207,11 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const int j = tid + i * C::THREADS;
+#if defined(MSPMV_WHATIF) && MSPMV_WHATIF == 2
+            if (j < nnzs && xv[i] == T(-1)) s_val[off_v + j] = xv[i];  // timing probe only: no product stores
+#else
             if (j < nnzs) s_val[off_v + j] *= xv[i];
+#endif
         }
     }
     // ---- row-end flags: merge item p = row_end[r] - y0 + r is the end of local row r ------------
@@ -223,10 +231,24 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     for (int k = lane; k < NW * IPT; k += 32)
         if (k < warp * IPT) before_warp += __popc(s_bits[k]);  // warp w owns words [w*IPT, (w+1)*IPT)
     before_warp = __reduce_add_sync(kFull, before_warp);
+#if defined(MSPMV_PREFIX_SHFL)
+    // whole words of my warp before mine: lane k < IPT counts word k of the warp, 4-step scan, pick mine
+    int wcnt = lane < IPT ? __popc(s_bits[warp * IPT + lane]) : 0;
+    int wpre = wcnt;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        int v = __shfl_up_sync(kFull, wpre, d);
+        if (lane >= d) wpre += v;
+    }
+    const int rel = (diag >> 5) - warp * IPT;  // my first word, relative to the warp's first word
+    int in_warp = __shfl_sync(kFull, wpre - wcnt, rel) + __popc(w0 & ((1u << (diag & 31)) - 1u));
+#else
+    // whole words of my warp before mine (independent broadcast loads), plus the low part of my word
     int in_warp = __popc(w0 & ((1u << (diag & 31)) - 1u));
 #pragma unroll
     for (int k = 0; k < IPT - 1; ++k)
         if (warp * IPT + k < (diag >> 5)) in_warp += __popc(s_bits[warp * IPT + k]);
+#endif
     const int xs = before_warp + in_warp;
 
     // ---- serial walk over my IPT merge items (cpu_spmv.cpp:324-340; agent_spmv_orig.cuh:557-578)
@@ -237,7 +259,13 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const bool is_end = (bits >> i) & 1u;
+#if defined(MSPMV_WHATIF) && MSPMV_WHATIF == 1
+        if (!is_end && i < my_items) running += s_val[off_v + min(diag + i, nnzs - 1)];  // timing probe only: conflict-free, WRONG
+#elif defined(MSPMV_WHATIF) && MSPMV_WHATIF == 2
+        if (!is_end && i < my_items) running += T(ny);  // timing probe only: no product loads, WRONG
+#else
         if (!is_end && i < my_items) running += s_val[ny];
+#endif
         ny += is_end ? 0 : 1;
         sums[i] = running;
         if (is_end) running = T(0);
@@ -279,10 +307,12 @@ __global__ __launch_bounds__(256) void carry_fixup_block_kernel(const int* __res
                                                                 const T* __restrict__ carry_vals, int n,
                                                           int num_rows, T* __restrict__ y, T alpha,
                                                           int* __restrict__ carry2_rows,
-                                                          T* __restrict__ carry2_vals)
+                                                          T* __restrict__ carry2_vals,
+                                                          unsigned int* __restrict__ ticket)
 {
     constexpr int FIX = 256;
     __shared__ Seg<T> s_warp[FIX / 32];
+    __shared__ bool s_last;
     const int tid = threadIdx.x;
     const int i = blockIdx.x * FIX + tid;
     const int row = i < n ? carry_rows[i] : INT_MAX;
@@ -325,6 +355,26 @@ __global__ __launch_bounds__(256) void carry_fixup_block_kernel(const int* __res
         } else if (row != next_row && row < num_rows) {
             y[row] += AXPBY ? alpha * run_sum : run_sum;
         }
+    }
+
+    // Level 2 in the same launch: the last block to finish (ticket counter cleared by the search
+    // kernel) folds the per-block carries.  Runs are short here (a row must span > FIX tiles to
+    // put two entries in one run); the thread owning the first entry of a run sums it left to
+    // right and adds it to y once -- the order of the CPU loop cpu_spmv.cpp:348-352.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nb = gridDim.x;
+    for (int b = tid; b < nb; b += FIX) {
+        const int r2 = carry2_rows[b];
+        if (r2 >= num_rows) continue;
+        if (b > 0 && carry2_rows[b - 1] == r2) continue;  // not the head of this row's run
+        T sum = carry2_vals[b];
+        for (int j = b + 1; j < nb && carry2_rows[j] == r2; ++j) sum += carry2_vals[j];
+        y[r2] += AXPBY ? alpha * sum : sum;
     }
 }
 

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-for v in "" merge-spmv_b200/variants/lib_evictlast.so; do
-for a in "--workload uniform_1m_64" "--workload uniform_1m_64 --cols 8388608" "--workload powerlaw_2m" "--workload banded_10m" "--workload powerlaw_20m --steps 30"; do
-MSPMV_LIB=$v timeout 200 python bench.py $a --no-cpu-baseline --no-e2e > gpurun_out/tmp.log 2>&1; python - <<PY
+for v in merge-spmv_b200/variants/lib_whatif2.so; do
+for a in "--workload uniform_1m_64" "--workload powerlaw_2m" "--workload banded_10m"; do
+MSPMV_LIB=$v timeout 200 python bench.py $a --no-cpu-baseline --no-e2e --steps 200 2>&1 | tail -1 > gpurun_out/tmp.log; python - <<PY
 import json
 l=open("gpurun_out/tmp.log").read().strip().splitlines()[-1]
 try:
