@@ -207,11 +207,7 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const int j = tid + i * C::THREADS;
-#if defined(MSPMV_WHATIF) && MSPMV_WHATIF == 2
-            if (j < nnzs && xv[i] == T(-1)) s_val[off_v + j] = xv[i];  // timing probe only: no product stores
-#else
             if (j < nnzs) s_val[off_v + j] *= xv[i];
-#endif
         }
     }
     // ---- row-end flags: merge item p = row_end[r] - y0 + r is the end of local row r ------------
@@ -259,13 +255,7 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const bool is_end = (bits >> i) & 1u;
-#if defined(MSPMV_WHATIF) && MSPMV_WHATIF == 1
-        if (!is_end && i < my_items) running += s_val[off_v + min(diag + i, nnzs - 1)];  // timing probe only: conflict-free, WRONG
-#elif defined(MSPMV_WHATIF) && MSPMV_WHATIF == 2
-        if (!is_end && i < my_items) running += T(ny);  // timing probe only: no product loads, WRONG
-#else
         if (!is_end && i < my_items) running += s_val[ny];
-#endif
         ny += is_end ? 0 : 1;
         sums[i] = running;
         if (is_end) running = T(0);
