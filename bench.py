@@ -61,7 +61,7 @@ def workload_spec(name, n_gpus):
 def build_row_offsets(kind, p):
     from merge_spmv_b200 import generators as gen
 
-    if kind == "uniform":
+    if kind in ("uniform", "uniform_local"):
         return gen.uniform_row_offsets(p["rows"], p["nnz_per_row"]), p["cols"], None
     if kind == "powerlaw":
         lengths, alpha = gen.powerlaw_row_lengths(p["rows"], min(p["max_row"], p["cols"]), p["target_nnz"])
@@ -72,10 +72,11 @@ def build_row_offsets(kind, p):
 def fill(kind, row_offsets, cols, k0, k1, dt, values, device, p):
     from merge_spmv_b200 import generators as gen
 
-    return gen.fill_nonzeros(row_offsets, cols, k0, k1, kind="banded" if kind == "banded" else "stratified",
-                             dtype=dt, values=values, device=device,
+    gkind = {"banded": "banded", "uniform_local": "local"}.get(kind, "stratified")
+    return gen.fill_nonzeros(row_offsets, cols, k0, k1, kind=gkind, dtype=dt, values=values, device=device,
                              half_bandwidth=p.get("half_bandwidth", 3),
-                             seed={"uniform": 0x5EED0001, "powerlaw": 0x5EED0003, "banded": 0x5EED0004}[kind])
+                             seed={"uniform": 0x5EED0001, "uniform_local": 0x5EED0001, "powerlaw": 0x5EED0003,
+                                   "banded": 0x5EED0004}[kind])
 
 
 def algorithmic_bytes(rows, cols, nnz, vb):
@@ -412,7 +413,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64" if vb == 8 else "f32", "data": "synthetic",
             "config": {"workload": name, "rows": rows, "cols": cols, "nnz": nnz, "values": args.values,
-                       "columns": "banded" if kind == "banded" else "stratified-uniform, sorted, distinct",
+                       "columns": {"banded": "banded", "uniform_local": "stratified within a 4096-column window around the diagonal"}.get(
+                           kind, "stratified-uniform over all columns, sorted, distinct"),
                        "parallelism": f"merge-path shards x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
                        "engine": args.engine or "tile", "cuda_graph": use_graph},

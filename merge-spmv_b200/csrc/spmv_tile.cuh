@@ -50,6 +50,7 @@ struct TileCfg {
     static constexpr int TILE = THREADS * IPT;    // merge items per block
     static constexpr int BW = TILE / 32 + 2;      // bitmap words
     static constexpr int FIX = 256;               // carries per fix-up block
+    static constexpr int LOCAL_SPAN = 32768;      // a warp whose columns span fewer elements than this lets its gathers allocate in L1
     static constexpr int ROWCAP = 384;            // row offsets staged in shared memory; tiles with more read them from L2
     static_assert(TILE % 32 == 0 && (IPT & 1) == 1 && IPT < 32, "bitmap layout");
 };
@@ -83,9 +84,11 @@ __global__ void diagonal_search_kernel(const int* __restrict__ row_end_offsets, 
 // L1 capacity is what bounds the number of misses in flight -- profiles/microbench_r01.txt); and
 // mark it L2::evict_last while the value / index / row-offset streams are L2::evict_first, so x --
 // the only reused data -- stays L2-resident even when it is tens of MB (profiles/tuning_r01.txt:
-// 20M-column power-law 12.98 -> 5.78 ms).  Flavours: 0 = __ldg, 2 = no_allocate, 3 = + evict_last.
+// 20M-column power-law 12.98 -> 5.78 ms).  Flavours: 0 = __ldg, 2 = no_allocate, 3 = + evict_last,
+// 4 = L1-allocating + evict_last, 5 = per-warp choice between 3 and 4 by column span (shipped: a
+// 4096-column-window matrix runs 0.419 ms with 3, 0.273 ms with 4/5; random columns prefer 3).
 #ifndef MSPMV_GATHER_FLAVOUR
-#define MSPMV_GATHER_FLAVOUR 3
+#define MSPMV_GATHER_FLAVOUR 5
 #endif
 __device__ __forceinline__ uint64_t l2_policy_evict_last()
 {
@@ -96,13 +99,33 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
 __device__ __forceinline__ float ld_gather(const float* p, uint64_t pol)
 {
     float v;
+#if MSPMV_GATHER_FLAVOUR == 4
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+#endif
     return v;
 }
 __device__ __forceinline__ double ld_gather(const double* p, uint64_t pol)
 {
     double v;
+#if MSPMV_GATHER_FLAVOUR == 4
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+#endif
+    return v;
+}
+__device__ __forceinline__ float ld_gather_l1(const float* p, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_gather_l1(const double* p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ float ld_gather(const float* p)
@@ -196,7 +219,27 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
             const int j = tid + i * C::THREADS;
             cidx[i] = j < nnzs ? s_col[off_c + j] : -1;
         }
-#if MSPMV_GATHER_FLAVOUR == 3
+#if MSPMV_GATHER_FLAVOUR == 5
+        // x is the only reused data: keep it in L2 (evict_last).  L1: a warp whose columns span a
+        // narrow range re-uses lines (banded / FEM-like locality) and lets them allocate; a warp with
+        // scattered columns has no L1 reuse, and there L1 capacity only limits the misses in flight,
+        // so its gathers do not allocate.  Warp-uniform decision from two sampled columns per thread.
+        const uint64_t keep = l2_policy_evict_last();
+        int cmin = cidx[0] >= 0 ? cidx[0] : INT_MAX, cmax = cidx[0];
+        if (cidx[IPT - 1] >= 0) {
+            cmin = min(cmin, cidx[IPT - 1]);
+            cmax = max(cmax, cidx[IPT - 1]);
+        }
+        cmin = __reduce_min_sync(kFull, cmin);
+        cmax = __reduce_max_sync(kFull, cmax);
+        if (cmax - cmin < C::LOCAL_SPAN) {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? ld_gather_l1(x + cidx[i], keep) : T(0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? ld_gather(x + cidx[i], keep) : T(0);
+        }
+#elif MSPMV_GATHER_FLAVOUR >= 3
         const uint64_t keep = l2_policy_evict_last();  // x is the only reused data: keep it in L2
 #pragma unroll
         for (int i = 0; i < IPT; ++i) xv[i] = cidx[i] >= 0 ? ld_gather(x + cidx[i], keep) : T(0);

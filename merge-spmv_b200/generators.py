@@ -117,9 +117,11 @@ def _rows_of(row_offsets_dev64, k):
 
 
 def fill_nonzeros(row_offsets, cols, k0, k1, *, kind, dtype, values="ones", seed=0x5EED0001,
-                  half_bandwidth=3, device="cpu", chunk=1 << 25, out_col=None, out_val=None):
+                  half_bandwidth=3, device="cpu", chunk=1 << 25, out_col=None, out_val=None, window=4096):
     """Column indices (int32) and values of nonzeros k0..k1-1 of the matrix whose full
-    row_offsets is given.  kind: "stratified" (uniform & power-law rows) or "banded"."""
+    row_offsets is given.  kind: "stratified" (uniform & power-law rows: columns over all of
+    [0, cols)), "local" (same stratified draw, but inside a `window`-wide column window centred on
+    the row -- FEM-like locality) or "banded"."""
     n = k1 - k0
     col = out_col if out_col is not None else torch.empty(n, dtype=torch.int32, device=device)
     val = out_val if out_val is not None else torch.empty(n, dtype=dtype, device=device)
@@ -138,6 +140,14 @@ def fill_nonzeros(row_offsets, cols, k0, k1, *, kind, dtype, values="ones", seed
             hi = ((j + 1) * cols) // length
             h = _lsr(splitmix64(k + _s64(seed)), 1)
             c = lo + h % torch.clamp(hi - lo, min=1)
+        elif kind == "local":
+            length = ro64[row + 1] - start
+            w = min(window, cols)
+            w0 = torch.clamp(row * cols // max(ro64.numel() - 1, 1) - w // 2, min=0, max=cols - w)
+            lo = (j * w) // length
+            hi = ((j + 1) * w) // length
+            h = _lsr(splitmix64(k + _s64(seed)), 1)
+            c = w0 + lo + h % torch.clamp(hi - lo, min=1)
         else:
             raise ValueError(kind)
         col[c0 - k0:c1 - k0] = c.to(torch.int32)
@@ -276,6 +286,9 @@ CONFIGS = {
     # name: (kind, dtype, params)
     "cpu_uniform_16k": ("uniform", torch.float64, dict(rows=16384, cols=16384, nnz_per_row=32)),
     "uniform_1m_64": ("uniform", torch.float64, dict(rows=1 << 20, cols=1 << 20, nnz_per_row=64)),
+    # same shape, columns drawn inside a 4096-wide window around the diagonal: shows the kernel
+    # without the random-gather ceiling (SURVEY.md section 8d asks for a local-column variant)
+    "uniform_1m_64_local": ("uniform_local", torch.float64, dict(rows=1 << 20, cols=1 << 20, nnz_per_row=64)),
     "powerlaw_2m": ("powerlaw", torch.float32, dict(rows=2_000_000, cols=2_000_000, max_row=1_000_000,
                                                    target_nnz=200_000_000)),
     "banded_10m": ("banded", torch.float64, dict(rows=10_000_000, half_bandwidth=3)),
