@@ -2,7 +2,8 @@
 //
 // Reference behaviour being re-implemented (file:line in /root/reference):
 //   MergePathSearch            cub/thread/thread_search.cuh:53-84 == cpu_spmv.cpp:223-245
-//   per-thread merge walk      cub/agent/agent_spmv_orig.cuh:557-578 (staged), :327-358 (direct)
+//   per-thread merge walk      cub/agent/agent_spmv_orig.cuh:557-578 (staged), :327-358 (direct) --
+//                              re-expressed as a bitmap-driven unrolled loop inside the kernels
 //   reduce-by-key scan op      cub/thread/thread_operators.cuh:278-302 (ReduceByKeyOp)
 //   block reduce-by-key        agent_spmv_orig.cuh:583-626 (BlockScan of KeyValuePair)
 // The block-wide scan of (row, partial) pairs is replaced by a warp-shuffle segmented scan of
@@ -126,54 +127,6 @@ __device__ __forceinline__ void block_seg_scan_exclusive(Seg<T> in, Seg<T> carry
     }
     excl = seg_combine(before, prev);
     total = run;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Per-thread merge walk over IPT consecutive merge items of a tile.
-//   row_end(i)   absolute nonzero index at which local row i ends; row_end(nrows) must be a
-//                sentinel >= any nonzero index (INT_MAX) -- this replaces the reference's read
-//                of one element past the tile
-//   prod(j)      value*x[col] of local nonzero j (tile-relative)
-//   out(i, v)    store the finished sum of local row i
-// Produces this thread's scan element (ended, tail) and, for the first row that ends inside the
-// thread's span, (head_row, head_val), which still lacks the carry-in from earlier threads.
-// ---------------------------------------------------------------------------------------------
-template <typename T, int IPT, typename RowEndFn, typename ProdFn, typename OutFn>
-__device__ __forceinline__ void thread_merge_walk(int diag, int items, int nrows, int nnzs, int y0,
-                                                  RowEndFn row_end, ProdFn prod, OutFn out,
-                                                  Seg<T>& elem, int& head_row, T& head_val)
-{
-    diag = min(diag, items);
-    int2 c = merge_path_search(diag, row_end, nrows, nnzs, y0);
-    int tx = c.x;        // local row
-    int ty = y0 + c.y;   // absolute nonzero index
-    int cur_end = row_end(tx);
-    T running = T(0);
-    elem.ended = 0;
-    head_row = 0;
-    head_val = T(0);
-
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        if (diag + i < items) {
-            if (ty < cur_end) {
-                running += prod(ty - y0);
-                ++ty;
-            } else {
-                if (!elem.ended) {
-                    elem.ended = 1;
-                    head_row = tx;
-                    head_val = running;
-                } else {
-                    out(tx, running);
-                }
-                running = T(0);
-                ++tx;
-                cur_end = row_end(tx);
-            }
-        }
-    }
-    elem.val = running;
 }
 
 // y = alpha*sum + beta*y_old epilogue (SpmvGold, gpu_spmv.cu:72-92); AXPBY=false is y = sum.
