@@ -17,7 +17,7 @@
 
 using namespace mspmv_host;
 
-static bool g_quiet = false, g_verbose = false;
+static bool g_quiet = false;
 
 #define CUDA_EXIT(e)                                                                              \
     do {                                                                                          \
@@ -237,7 +237,6 @@ int main(int argc, char** argv)
     }
     int timing_iterations = -1, dev = 0;
     float alpha = 1.0f, beta = 0.0f;
-    g_verbose = args.CheckCmdLineFlag("v");
     g_quiet = args.CheckCmdLineFlag("quiet");
     const bool fp32 = args.CheckCmdLineFlag("fp32");
     args.GetCmdLineArgument("i", timing_iterations);
