@@ -240,7 +240,7 @@ def main():
     ap.add_argument("--engine", default=None, choices=[None, "stream", "tile", "auto"])
     ap.add_argument("--cols", type=int, default=None, help="override the column count (x length) of the workload")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay each step as one CUDA graph (auto: on for N>1, where the collective's host cost matters)")
+                    help="replay each step (3 kernels, plus the collective and carry fold at N>1) as one CUDA graph; auto = on")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -291,7 +291,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
+    use_graph = args.graph in ("on", "auto")
     c0 = L.mspmv_launch_count()
     op(x)  # one eager step: also counts this library's kernels per step (graph replays bypass the counter)
     launches_per_step = L.mspmv_launch_count() - c0
