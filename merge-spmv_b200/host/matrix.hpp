@@ -610,6 +610,11 @@ void maybe_dump_csr(const CommandLineArgs& args, const Csr<V>& m)
     std::string path;
     args.GetCmdLineArgument("dumpcsr", path);
     if (!path.empty()) dump_csr(path, m);
+    // --writemtx=<path>: save the matrix as Matrix-Market, e.g. to feed a synthetic config to the
+    // reference's own binaries through --mtx=
+    std::string mtx_out;
+    args.GetCmdLineArgument("writemtx", mtx_out);
+    if (!mtx_out.empty()) write_matrix_market(mtx_out, m);
 }
 
 }  // namespace mspmv_host

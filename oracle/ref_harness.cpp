@@ -135,6 +135,9 @@ int ref_compare_results_f64(double* computed, double* reference, int len) {
 
 int ref_num_procs(void) { return omp_get_num_procs(); }
 
+// The reference driver's own main() (cpu_spmv.cpp:682-747), for pinning the CLI / CSV contract.
+int ref_cpu_spmv_main(int argc, char** argv) { return reference_cpu_spmv_main(argc, argv); }
+
 // ---- matrix builders (fp64 values): kind 0 = Matrix-Market file, 1 = grid2d(w), 2 = grid3d(w),
 // 3 = wheel(spokes), 4 = dense(rows=a, cols=b).  Returns 0 and fills dims; then ref_built_copy.
 int ref_build(int kind, const char* path, int a, int b, int* dims /* rows, cols, nnz */) {

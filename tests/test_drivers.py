@@ -3,6 +3,7 @@ golden CSR the reference's own code produced, the CLI/CSV contract, and (GPU) th
 self-check.  The cpu_spmv driver is a separate CPU tool and runs here without a GPU."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -85,6 +86,52 @@ def test_synthetic_families_match_python_generators(tmp_path):
     rows, cols, nnz, ro, col, val = read_dump(dump)
     p = gen.powerlaw(3000, 3000, 500, 60000)
     assert np.array_equal(ro, p.row_offsets.numpy()) and np.array_equal(col, p.col.numpy())
+
+
+def test_matrix_market_round_trip_and_corpus_script(tmp_path):
+    """--writemtx output re-read through --mtx gives the same CSR (so synthetic configs can be fed to
+    the reference's own binaries), and eval_csrmv.sh prints the reference's CSV header + one line
+    per .mtx file (eval_csrmv.sh:8,14-17)."""
+    a, b = tmp_path / "a.bin", tmp_path / "b.bin"
+    corpus = tmp_path / "corpus"
+    corpus.mkdir()
+    mtx = corpus / "u.mtx"
+    assert run([CPU, "--uniform=5", "--rows=300", "--values=random", "--quiet", "--i=1", f"--dumpcsr={a}",
+                f"--writemtx={mtx}"]).returncode == 0
+    assert run([CPU, f"--mtx={mtx}", "--quiet", "--i=1", f"--dumpcsr={b}"]).returncode == 0
+    ra, rb = read_dump(a), read_dump(b)
+    assert ra[:3] == rb[:3]
+    for x, y in zip(ra[3:], rb[3:]):
+        assert np.array_equal(x, y)
+    assert run([CPU, "--grid2d=12", "--quiet", "--i=1", f"--writemtx={corpus / 'g.mtx'}"]).returncode == 0
+    r = run([os.path.join(PKG, "eval_csrmv.sh"), str(corpus), "cpu_spmv"])
+    lines = [l for l in r.stdout.strip().splitlines() if l.strip()]
+    assert lines[0].startswith("file, num_rows, num_cols, num_nonzeros, row_length_mean")
+    assert len(lines) == 3 and all("Merge CsrMV" in l for l in lines[1:])
+
+
+def _reference_driver_stdout(args):
+    """stdout of the reference's own cpu_spmv main() (compiled into oracle/_ref), in a subprocess."""
+    import oracle
+    code = ("import ctypes as C, sys; L = C.CDLL(%r); a = [b'cpu_spmv'] + [s.encode() for s in sys.argv[1:]]; "
+            "argv = (C.c_char_p * len(a))(*a); L.ref_cpu_spmv_main(len(a), argv); "
+            "C.CDLL(None).fflush(None)" % oracle.Reference.path())
+    return subprocess.run([sys.executable, "-c", code] + args, capture_output=True, text=True, timeout=300).stdout
+
+
+@pytest.mark.parametrize("flags", [["--grid2d=40"], ["--grid3d=12"], ["--dense=16", "--fp32"]])
+def test_csv_contract_matches_reference_driver(ref, flags):
+    """--quiet line of our cpu_spmv vs the reference's own main(): same label and the same seven
+    statistics fields, character for character; the method name "Merge CsrMV" with four numbers.
+    (The reference also prints an "MKL CsrMV" group first, cpu_spmv.cpp:649-652; MKL is out of scope.)"""
+    theirs = [f.strip() for f in _reference_driver_stdout(flags + ["--quiet", "--i=2"]).strip().rstrip(",").split(",")]
+    ours = [f.strip() for f in run([CPU] + flags + ["--quiet", "--i=2"]).stdout.strip().rstrip(",").split(",")]
+    assert ours[:8] == theirs[:8], (ours[:8], theirs[:8])
+    assert "MKL CsrMV" in theirs and theirs[theirs.index("Merge CsrMV") - 5] == "MKL CsrMV"
+    i, j = ours.index("Merge CsrMV"), theirs.index("Merge CsrMV")
+    assert len(ours[i + 1:]) == len(theirs[j + 1:]) == 4
+    for a in ours[i + 1:]:
+        float(a)
 
 
 def test_cpu_driver_pass_and_threads():
