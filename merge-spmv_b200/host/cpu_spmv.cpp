@@ -76,9 +76,6 @@ static void run_tests(const CommandLineArgs& args, V alpha, V beta, int timing_i
 {
     Csr<V> a = build_from_args<V>(args, g_quiet, false);
     maybe_dump_csr(args, a);
-    if (timing_iterations == -1)  // cpu_spmv.cpp:613
-        timing_iterations = (int)std::min(200000ull, std::max(100ull, (16ull << 30) / (unsigned long long)std::max(a.num_nonzeros, 1)));
-    if (!g_quiet) std::printf("\t%d timing iterations\n", timing_iterations);
     stats(a).display(!g_quiet);
     if (!g_quiet) {
         std::printf("\n");
@@ -86,6 +83,10 @@ static void run_tests(const CommandLineArgs& args, V alpha, V beta, int timing_i
         std::printf("\n\n");
     }
     std::fflush(stdout);
+    if (timing_iterations == -1) {  // cpu_spmv.cpp:609-615: printed after the statistics, only when adaptive
+        timing_iterations = (int)std::min(200000ull, std::max(100ull, (16ull << 30) / (unsigned long long)std::max(a.num_nonzeros, 1)));
+        if (!g_quiet) std::printf("\t%d timing iterations\n", timing_iterations);
+    }
     std::vector<V> x(a.num_cols, V(1)), y_in(a.num_rows, V(1)), y_ref(a.num_rows), y(a.num_rows);
     if (args.CheckCmdLineFlag("randx"))
         for (int c = 0; c < a.num_cols; ++c) x[c] = (V)hashed_value((uint64_t)c, 0x5EED00FFull);

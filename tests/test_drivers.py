@@ -134,6 +134,20 @@ def test_csv_contract_matches_reference_driver(ref, flags):
         float(a)
 
 
+def test_human_output_matches_reference_driver(ref):
+    """Non-quiet mode: the statistics block, the histogram and the perf line grammar are the
+    reference's (sparse_matrix.h:75-89,919-956; cpu_spmv.cpp:515-520)."""
+    import re
+    flags = ["--grid3d=10", "--i=2", "--threads=2"]
+    theirs = _reference_driver_stdout(flags).splitlines()
+    ours = run([CPU] + flags).stdout.splitlines()
+    keep = lambda ls: [l for l in ls if re.search(r"num_rows:|num_cols:|num_nonzeros:|row_length_|CSR matrix \(|Degree 1e|Using 2 threads", l)]
+    assert keep(ours) == keep(theirs) and len(keep(ours)) >= 11
+    perf = re.compile(r"^fp64: \d+\.\d{4} setup ms, \d+\.\d{4} avg ms, \d+\.\d{5} gflops, \d+\.\d{3} effective GB/s$")
+    assert any(perf.match(l) for l in ours) and any(perf.match(l) for l in theirs)
+    assert any(l.strip() == "PASS" for l in ours)
+
+
 def test_cpu_driver_pass_and_threads():
     r = run([CPU, "--grid3d=30", "--i=5", "--threads=3"])
     assert r.returncode == 0 and "PASS" in r.stdout and "Using 3 threads" in r.stdout
