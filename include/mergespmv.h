@@ -156,6 +156,9 @@ int mspmv_host_free(void* p);
  * 5. Introspection.
  * ----------------------------------------------------------------------------------------- */
 int mspmv_version(void); /* major*100 + minor */
+/* PTX/SASS version the kernels were compiled for, in cub::PtxVersion units (util_device.cuh:118-160:
+ * major*100 + minor*10, e.g. 1000 for sm_100a); written to *ptx_version. */
+int mspmv_ptx_version(int* ptx_version);
 /* Kernel launches issued by this library since load (all entry points). */
 uint64_t mspmv_launch_count(void);
 /* Launch geometry mspmv_csrmv_* uses for a shape: out[0] = swaths (threadblocks),

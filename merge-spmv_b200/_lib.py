@@ -28,6 +28,7 @@ SIGNATURES = {
     "mspmv_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "mspmv_host_free": (_i, [_vp]),
     "mspmv_version": (_i, []),
+    "mspmv_ptx_version": (_i, [C.POINTER(_i)]),
     "mspmv_launch_count": (C.c_uint64, []),
     "mspmv_csrmv_config": (_i, [_i, _i, _i, C.POINTER(_i)]),
     "mspmv_error_string": (C.c_char_p, [_i]),

@@ -544,6 +544,15 @@ int mspmv_host_alloc(void** out, size_t bytes) { return (int)cudaMallocHost(out,
 int mspmv_host_free(void* p) { return (int)cudaFreeHost(p); }
 
 int mspmv_version(void) { return MSPMV_VERSION_MAJOR * 100 + MSPMV_VERSION_MINOR; }
+
+int mspmv_ptx_version(int* ptx_version)
+{
+    if (!ptx_version) return (int)cudaErrorInvalidValue;
+    cudaFuncAttributes attr;
+    MSPMV_TRY(cudaFuncGetAttributes(&attr, spmv_tile_kernel<double, false>));
+    *ptx_version = attr.ptxVersion * 10;
+    return 0;
+}
 uint64_t mspmv_launch_count(void) { return g_launches.load(); }
 
 int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out)

@@ -262,8 +262,10 @@ int main(int argc, char** argv)
     cudaDeviceGetAttribute(&bus_width, cudaDevAttrGlobalMemoryBusWidth, dev);
     float device_giga_bandwidth = float(bus_width) * mem_clock_khz * 2 / 8 / 1000 / 1000;  // utils.h:491
     if (!g_quiet) {
-        std::printf("Using device %d: %s (SM%d, %d SMs, %lld free / %lld total MB physmem, %.3f GB/s @ %d kHz mem clock, ECC %s)\n",
-                    dev, prop.name, prop.major * 100 + prop.minor * 10, prop.multiProcessorCount,
+        int ptx_version = 0;
+        mspmv_ptx_version(&ptx_version);
+        std::printf("Using device %d: %s (PTX version %d, SM%d, %d SMs, %lld free / %lld total MB physmem, %.3f GB/s @ %d kHz mem clock, ECC %s)\n",
+                    dev, prop.name, ptx_version, prop.major * 100 + prop.minor * 10, prop.multiProcessorCount,
                     (long long)free_mem / 1024 / 1024, (long long)total_mem / 1024 / 1024, device_giga_bandwidth,
                     mem_clock_khz, prop.ECCEnabled ? "on" : "off");
         std::fflush(stdout);
