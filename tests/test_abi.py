@@ -44,6 +44,15 @@ def test_no_cpu_fallback():
         ms.csrmv(ro, torch.zeros(1, dtype=torch.int32), torch.ones(1), torch.ones(1))
 
 
+def test_missing_library_fails_loudly():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import merge_spmv_b200 as ms\n"
+            "try:\n    ms.lib()\nexcept ms.MergeSpmvError as e:\n    print('LOUD', e)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       env=dict(os.environ, MSPMV_LIB="/nonexistent/libmergespmv.so"), timeout=120)
+    assert "LOUD" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
 def test_host_merge_path_search_matches_oracle(orc):
     rng = np.random.default_rng(17)
     L = ms.lib()
