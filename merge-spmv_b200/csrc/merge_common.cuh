@@ -82,6 +82,9 @@ __device__ __forceinline__ T shfl_up(T v, int d)
 template <typename T>
 __device__ __forceinline__ Seg<T> warp_seg_scan_inclusive(Seg<T> s, int lane)
 {
+    // short-row matrices: every lane closes a row, so every lane starts a new segment and the
+    // inclusive result is the lane's own element -- one vote instead of five shuffle rounds
+    if (__all_sync(kFull, s.ended)) return s;
 #pragma unroll
     for (int d = 1; d < kWarp; d <<= 1) {
         T v = shfl_up(s.val, d);

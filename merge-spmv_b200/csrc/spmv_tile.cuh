@@ -291,17 +291,28 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     const int xs = before_warp + in_warp;
 
     // ---- serial walk over my IPT merge items (cpu_spmv.cpp:324-340; agent_spmv_orig.cuh:557-578)
-    const int my_items = min(max(items - diag, 0), IPT);
     int ny = off_v + diag - xs;              // buffer position of my first product
     T sums[IPT];
     T running = T(0);
+    if (items == C::TILE) {                  // every tile but the last: all IPT items exist
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        const bool is_end = (bits >> i) & 1u;
-        if (!is_end && i < my_items) running += s_val[ny];
-        ny += is_end ? 0 : 1;
-        sums[i] = running;
-        if (is_end) running = T(0);
+        for (int i = 0; i < IPT; ++i) {
+            const bool is_end = (bits >> i) & 1u;
+            if (!is_end) running += s_val[ny];
+            ny += is_end ? 0 : 1;
+            sums[i] = running;
+            if (is_end) running = T(0);
+        }
+    } else {
+        const int my_items = min(max(items - diag, 0), IPT);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const bool is_end = (bits >> i) & 1u;
+            if (!is_end && i < my_items) running += s_val[ny];
+            ny += is_end ? 0 : 1;
+            sums[i] = running;
+            if (is_end) running = T(0);
+        }
     }
     Seg<T> elem, zero, excl, total;
     elem.val = running;
