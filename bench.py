@@ -348,7 +348,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tile_kernel" if (args.engine or "tile") != "stream" else "spmv_stream_kernel",
                 "algorithmic_bytes_per_launch": shard_bytes,
-                "note": "duration = whole step (search + tile + carry fix-up kernels; the tile kernel is 94.8% of it, profiles/launches_r01.csv), CUDA events"}
+                "note": "duration = whole step (search + tile + carry fix-up kernels; the tile kernel is 94.7% of it, profiles/launches_r01.csv), CUDA events"}
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------
     e2e = None
