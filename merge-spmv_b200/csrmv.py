@@ -111,7 +111,11 @@ def _temp_for(device, nbytes):
 
 def csrmv(row_offsets, column_indices, values, x, y=None, *, alpha=None, beta=None, num_cols=None,
           stream=None, debug_synchronous=False):
-    """Convenience wrapper: size query + temp blob (cached per device) + run.  Returns ``y``."""
+    """Convenience wrapper: size query + temp blob (cached per device) + run.  Returns ``y``.
+
+    The cached blob is shared by every call on that device, so calls must be stream-ordered with
+    respect to each other (like any CUB temp storage); use ``DeviceSpmv.CsrMV`` with your own blobs
+    to run several CsrMVs concurrently."""
     rows = row_offsets.numel() - 1
     nnz = values.numel()
     cols = int(num_cols) if num_cols is not None else x.numel()
