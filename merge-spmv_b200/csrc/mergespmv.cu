@@ -71,6 +71,10 @@ static Engine engine_from_env()
     return e;
 }
 
+#ifndef MSPMV_TILE_PREFETCH_DEFAULT
+#define MSPMV_TILE_PREFETCH_DEFAULT 0  // 0 = off (shipped); -1 = sm_count * 11
+#endif
+
 static inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 
 template <typename T>
@@ -126,6 +130,21 @@ static int post_launch(const char* name, dim3 grid, dim3 block, size_t smem, cud
     MSPMV_TRY(cudaPeekAtLastError());
     if (debug_sync) MSPMV_TRY(cudaStreamSynchronize(stream));
     return 0;
+}
+
+// Tiles of L2 prefetch lookahead for the tile engine: roughly the number of blocks resident on the
+// GPU, so a tile's slice is requested one block lifetime before the block that needs it starts.
+// MSPMV_TILE_PREFETCH overrides (0 = off).
+static int tile_prefetch_ahead()
+{
+    static int ahead = [] {
+        if (const char* e = std::getenv("MSPMV_TILE_PREFETCH")) return std::atoi(e);
+        return MSPMV_TILE_PREFETCH_DEFAULT;
+    }();
+    if (ahead >= 0) return ahead;
+    DeviceInfo di;
+    if (device_info(di)) return 0;
+    return di.sm_count * 11;
 }
 
 template <typename T, bool AXPBY>
@@ -186,7 +205,7 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     }
     spmv_tile_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
                                                           carry_vals, alpha, beta, num_rows, num_nonzeros, shift_v,
-                                                          shift_c, shift_r);
+                                                          shift_c, shift_r, tile_prefetch_ahead());
     rc = post_launch("spmv_tile_kernel", grid, block, 0, stream, debug_sync);
     if (rc) return rc;
     if (p.num_tiles > 1) {  // dispatch_spmv_orig.cuh:721

@@ -149,13 +149,30 @@ __device__ __forceinline__ double ld_gather(const double* p)
 #endif
 }
 
+// L2 prefetch of the aligned superset of elements [lo, hi) of an array (a pure hint: the tile that
+// will need it starts about one block lifetime later and then finds its slice in L2, not HBM).
+template <typename E>
+__device__ __forceinline__ void l2_prefetch_range(const E* __restrict__ base, int shift, int lo, int hi,
+                                                  int n_total)
+{
+    constexpr int GRAN = 16 / (int)sizeof(E);
+    if (lo >= hi) return;
+    int lo_al = lo - ((lo + shift) & (GRAN - 1));
+    int hi_al = hi + ((GRAN - ((hi + shift) & (GRAN - 1))) & (GRAN - 1));
+    if (lo_al < 0) lo_al += GRAN;
+    if (hi_al > n_total) hi_al -= GRAN;
+    if (lo_al >= hi_al) return;
+    const uint32_t bytes = (uint32_t)(hi_al - lo_al) * (uint32_t)sizeof(E);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + lo_al), "r"(bytes) : "memory");
+}
+
 // ---- step 2: one tile per threadblock
 template <typename T, bool AXPBY>
 __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     const T* __restrict__ values, const int* __restrict__ row_offsets,
     const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
     const int2* __restrict__ coords, int* __restrict__ carry_rows, T* __restrict__ carry_vals, T alpha,
-    T beta, int num_rows, int num_nonzeros, int shift_v, int shift_c, int shift_r)
+    T beta, int num_rows, int num_nonzeros, int shift_v, int shift_c, int shift_r, int prefetch_ahead)
 {
     using C = TileCfg<T>;
     constexpr int IPT = C::IPT;
@@ -206,6 +223,16 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
         if (lane == 0) {
             if (b) mbar_arrive_expect_tx(&s_bar, b);
             else mbar_arrive(&s_bar);
+        }
+    }
+    // ---- L2 prefetch for the tile `prefetch_ahead` tiles later (warp 1, off the critical path) ---
+    if (prefetch_ahead > 0 && warp == 1 && lane == 0) {
+        const long long ft = (long long)tile + prefetch_ahead;
+        if (ft < (long long)gridDim.x) {
+            const int2 f0 = __ldg(coords + ft), f1 = __ldg(coords + ft + 1);
+            l2_prefetch_range<T>(values, shift_v, f0.y, f1.y, num_nonzeros);
+            l2_prefetch_range<int>(column_indices, shift_c, f0.y, f1.y, num_nonzeros);
+            l2_prefetch_range<int>(row_offsets, shift_r, f0.x + 1, f1.x + 1, num_rows + 1);
         }
     }
     mbar_wait(&s_bar, 0);
