@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx_sm100.cuh"
+
 namespace mspmv {
 
 constexpr int kWarp = 32;
@@ -119,7 +121,7 @@ __device__ __forceinline__ void block_seg_scan_exclusive(Seg<T> in, Seg<T> carry
         prev.val = T(0);
         prev.ended = 0;
     }
-    asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(NWARPS * 32) : "memory");
+    named_bar_sync(barrier_id, NWARPS * 32);
 
     Seg<T> run = carry_in;
     Seg<T> before = carry_in;

@@ -1,0 +1,182 @@
+// ptx_sm100.cuh -- every inline-PTX instruction the sm_100a kernels use, behind one-line wrappers:
+// mbarrier, cp.async.bulk (TMA; SASS UBLKCP / UBLKPF), cp.async (LDGSTS), named barriers, L2 cache
+// policies and the cache-hinted x gathers.  Kernel code contains no asm of its own, so this file is
+// the complete list of architecture-specific instructions of the library.
+//
+// Test seam: tests/emu/ (a host-side SIMT interpreter used ONLY by the CPU test-suite to run the
+// kernel logic without a GPU) replaces this header through MSPMV_PTX_HEADER.  The product build
+// never defines it; libmergespmv.so contains only the code below.
+#pragma once
+#ifdef MSPMV_PTX_HEADER
+#include MSPMV_PTX_HEADER
+#else
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mspmv {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+// 4- or 8-byte asynchronous global -> shared copy (LDGSTS): the x gather, no register staging
+template <int BYTES>
+__device__ __forceinline__ void cp_async_gather(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "n"(BYTES)
+                 : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (counted in the
+// barrier's expected arrivals: .noinc)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// L2 prefetch of `bytes` (multiple of 16) at a 16-byte-aligned global address (SASS UBLKPF.L2)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
+// x gather: read-only path; do not keep the line in L1 after use (random gathers have no reuse and
+// L1 capacity is what bounds the number of misses in flight -- profiles/microbench_r01.txt); and
+// mark it L2::evict_last while the value / index / row-offset streams are L2::evict_first, so x --
+// the only reused data -- stays L2-resident even when it is tens of MB (profiles/tuning_r01.txt:
+// 20M-column power-law 12.98 -> 5.78 ms).  Flavours: 0 = __ldg, 2 = no_allocate, 3 = + evict_last,
+// 4 = L1-allocating + evict_last, 5 = per-warp choice between 3 and 4 by column span (shipped: a
+// 4096-column-window matrix runs 0.419 ms with 3, 0.273 ms with 4/5; random columns prefer 3).
+#ifndef MSPMV_GATHER_FLAVOUR
+#define MSPMV_GATHER_FLAVOUR 5
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float ld_gather(const float* p, uint64_t pol)
+{
+    float v;
+#if MSPMV_GATHER_FLAVOUR == 4
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+#endif
+    return v;
+}
+__device__ __forceinline__ double ld_gather(const double* p, uint64_t pol)
+{
+    double v;
+#if MSPMV_GATHER_FLAVOUR == 4
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+#endif
+    return v;
+}
+__device__ __forceinline__ float ld_gather_l1(const float* p, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_gather_l1(const double* p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_gather(const float* p)
+{
+#if MSPMV_GATHER_FLAVOUR == 2
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double ld_gather(const double* p)
+{
+#if MSPMV_GATHER_FLAVOUR == 2
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
+}  // namespace mspmv
+
+#endif  // MSPMV_PTX_HEADER

@@ -33,97 +33,9 @@
 #include <limits.h>
 
 #include "merge_common.cuh"
+#include "tma_stage.cuh"
 
 namespace mspmv {
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers (mbarrier + bulk async copy)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                         uint64_t* bar, uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-// 4- or 8-byte asynchronous global -> shared copy (LDGSTS): the x gather, no register staging
-template <int BYTES>
-__device__ __forceinline__ void cp_async_gather(void* dst_smem, const void* src_gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
-                 "n"(BYTES)
-                 : "memory");
-}
-// arrive on `bar` once all cp.async issued so far by this thread have landed (counted in the
-// barrier's expected arrivals: .noinc)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int threads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 // Geometry
@@ -217,81 +129,6 @@ __device__ __forceinline__ int2 warp_merge_path_search_global(int64_t diag64,
         hi = new_hi;
     }
     return make_int2(min(lo, num_rows), diag - lo);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Producer helper: stage elements [lo, hi) of a global array into a ring.
-// Ring position of element i is (i + shift) & mask where shift = element misalignment of the
-// array base w.r.t. 16 bytes, so 16-byte-aligned global addresses land on 16-byte-aligned ring
-// positions.  The aligned middle goes by one bulk copy (lane 0); the < 16-byte ragged ends are
-// copied by lanes 1..; returns the bulk byte count (valid in lane 0).  The range never wraps the
-// ring except through the ragged tail, which is masked per element.
-// ------------------------------------------------------------------------------------------------
-template <typename E>
-__device__ __forceinline__ uint32_t stage_range(const E* __restrict__ base, int shift, int lo, int hi,
-                                                E* ring, int mask, uint64_t* bar, uint64_t policy,
-                                                int lane, int pos_base = 0)
-{
-    constexpr int GRAN = 16 / (int)sizeof(E);
-    if (lo >= hi) return 0;
-    int lo_al = lo + ((GRAN - ((lo + shift) & (GRAN - 1))) & (GRAN - 1));  // first aligned index >= lo
-    int hi_al = hi - ((hi + shift) & (GRAN - 1));                          // last aligned index <= hi
-    uint32_t bytes = 0;
-    if (lo_al < hi_al) {
-        bytes = (uint32_t)(hi_al - lo_al) * (uint32_t)sizeof(E);
-    } else {
-        lo_al = hi;  // no aligned middle: everything is ragged head
-        hi_al = hi;
-    }
-    // ragged head [lo, lo_al) and tail [hi_al, hi): at most GRAN-1 elements each
-    int nhead = lo_al - lo, ntail = hi - hi_al;
-    if (lane < nhead) {
-        int i = lo + lane;
-        ring[((i + shift) & mask) - pos_base] = base[i];
-    } else if (lane >= 8 && lane - 8 < ntail) {
-        int i = hi_al + (lane - 8);
-        ring[((i + shift) & mask) - pos_base] = base[i];
-    }
-    if (lane == 0 && bytes)
-        bulk_g2s(ring + (((lo_al + shift) & mask) - pos_base), base + lo_al, bytes, bar, policy);
-    return bytes;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Stage elements [lo, hi) of a global array of n_total elements into a LINEAR buffer with one bulk
-// copy of the 16-byte-aligned superset [lo_al, hi_al) whenever that superset stays inside the
-// array (always, except possibly at the very first / last elements of the array, which fall back
-// to scalar copies by lanes 1..).  Element i lands at buf[(i + shift) - pos_base]; pos_base must
-// be the aligned-down position of lo and the buffer needs 16 bytes of slack at its end.
-// Returns the bulk byte count (valid in lane 0).
-// ------------------------------------------------------------------------------------------------
-template <typename E>
-__device__ __forceinline__ uint32_t stage_superset(const E* __restrict__ base, int shift, int lo, int hi,
-                                                   int n_total, E* buf, int pos_base, uint64_t* bar,
-                                                   uint64_t policy, int lane)
-{
-    constexpr int GRAN = 16 / (int)sizeof(E);
-    if (lo >= hi) return 0;
-    int lo_al = lo - ((lo + shift) & (GRAN - 1));                          // aligned index <= lo
-    int hi_al = hi + ((GRAN - ((hi + shift) & (GRAN - 1))) & (GRAN - 1));  // aligned index >= hi
-    if (lo_al < 0) {        // array starts mid-granule: copy the head by hand
-        lo_al += GRAN;
-        const int i = lo + lane;
-        if (i < min(lo_al, hi)) buf[i + shift - pos_base] = base[i];
-    }
-    if (hi_al > n_total) {  // array ends mid-granule: copy the tail by hand
-        hi_al -= GRAN;
-        const int i = max(hi_al, lo) + lane;
-        if (i < hi && hi_al >= lo_al) buf[i + shift - pos_base] = base[i];
-    }
-    if (lo_al >= hi_al) {
-        // no aligned middle at all (tiny array): everything not covered above goes by hand
-        for (int i = lo + lane; i < hi; i += 32) buf[i + shift - pos_base] = base[i];
-        return 0;
-    }
-    const uint32_t bytes = (uint32_t)(hi_al - lo_al) * (uint32_t)sizeof(E);
-    if (lane == 0) bulk_g2s(buf + (lo_al + shift - pos_base), base + lo_al, bytes, bar, policy);
-    return bytes;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@
 #include <limits.h>
 
 #include "merge_common.cuh"
-#include "spmv_stream.cuh"  // PTX wrappers (mbarrier, bulk copy) and stage_range()
+#include "tma_stage.cuh"  // stage_superset(): TMA bulk copies of aligned supersets
 
 namespace mspmv {
 
@@ -78,92 +78,6 @@ __global__ void diagonal_search_kernel(const int* __restrict__ row_end_offsets, 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
         coords[i] = merge_path_search_global(diagonals[i], row_end_offsets, num_rows, num_nonzeros);
-}
-
-// x gather: read-only path; do not keep the line in L1 after use (random gathers have no reuse and
-// L1 capacity is what bounds the number of misses in flight -- profiles/microbench_r01.txt); and
-// mark it L2::evict_last while the value / index / row-offset streams are L2::evict_first, so x --
-// the only reused data -- stays L2-resident even when it is tens of MB (profiles/tuning_r01.txt:
-// 20M-column power-law 12.98 -> 5.78 ms).  Flavours: 0 = __ldg, 2 = no_allocate, 3 = + evict_last,
-// 4 = L1-allocating + evict_last, 5 = per-warp choice between 3 and 4 by column span (shipped: a
-// 4096-column-window matrix runs 0.419 ms with 3, 0.273 ms with 4/5; random columns prefer 3).
-#ifndef MSPMV_GATHER_FLAVOUR
-#define MSPMV_GATHER_FLAVOUR 5
-#endif
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ float ld_gather(const float* p, uint64_t pol)
-{
-    float v;
-#if MSPMV_GATHER_FLAVOUR == 4
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-#else
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-#endif
-    return v;
-}
-__device__ __forceinline__ double ld_gather(const double* p, uint64_t pol)
-{
-    double v;
-#if MSPMV_GATHER_FLAVOUR == 4
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-#else
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-#endif
-    return v;
-}
-__device__ __forceinline__ float ld_gather_l1(const float* p, uint64_t pol)
-{
-    float v;
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ double ld_gather_l1(const double* p, uint64_t pol)
-{
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ld_gather(const float* p)
-{
-#if MSPMV_GATHER_FLAVOUR == 2
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
-__device__ __forceinline__ double ld_gather(const double* p)
-{
-#if MSPMV_GATHER_FLAVOUR == 2
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
-
-// L2 prefetch of the aligned superset of elements [lo, hi) of an array (a pure hint: the tile that
-// will need it starts about one block lifetime later and then finds its slice in L2, not HBM).
-template <typename E>
-__device__ __forceinline__ void l2_prefetch_range(const E* __restrict__ base, int shift, int lo, int hi,
-                                                  int n_total)
-{
-    constexpr int GRAN = 16 / (int)sizeof(E);
-    if (lo >= hi) return;
-    int lo_al = lo - ((lo + shift) & (GRAN - 1));
-    int hi_al = hi + ((GRAN - ((hi + shift) & (GRAN - 1))) & (GRAN - 1));
-    if (lo_al < 0) lo_al += GRAN;
-    if (hi_al > n_total) hi_al -= GRAN;
-    if (lo_al >= hi_al) return;
-    const uint32_t bytes = (uint32_t)(hi_al - lo_al) * (uint32_t)sizeof(E);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + lo_al), "r"(bytes) : "memory");
 }
 
 // ---- step 2: one tile per threadblock
