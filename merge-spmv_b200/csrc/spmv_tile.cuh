@@ -92,12 +92,12 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     constexpr int IPT = C::IPT;
     constexpr int NW = C::THREADS / 32;
     constexpr int GV = 16 / (int)sizeof(T);  // elements per 16 bytes
-    __shared__ alignas(128) T s_val[C::TILE + 2 * GV];
-    __shared__ alignas(128) int s_col[C::TILE + 8];
-    __shared__ alignas(128) int s_row[C::ROWCAP + 8];
-    __shared__ alignas(16) uint32_t s_bits[C::BW];
-    __shared__ alignas(16) Seg<T> s_warp[NW];
-    __shared__ alignas(8) uint64_t s_bar;
+    alignas(128) __shared__ T s_val[C::TILE + 2 * GV];
+    alignas(128) __shared__ int s_col[C::TILE + 8];
+    alignas(128) __shared__ int s_row[C::ROWCAP + 8];
+    alignas(16) __shared__ uint32_t s_bits[C::BW];
+    alignas(16) __shared__ Seg<T> s_warp[NW];
+    alignas(8) __shared__ uint64_t s_bar;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;

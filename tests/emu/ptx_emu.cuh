@@ -1,0 +1,124 @@
+// ptx_emu.cuh -- host stand-ins for the wrappers of merge-spmv_b200/csrc/ptx_sm100.cuh, used only by
+// the SIMT interpreter in tests/emu/ (see simt_emu.hpp).  They keep the *contracts* of the
+// instructions so that misuse is caught on the CPU:
+//   * cp.async.bulk: 16-byte aligned source and destination, size a multiple of 16; the destination
+//     is poisoned at issue and the data lands only when the mbarrier phase completes, so a kernel
+//     that reads staged data without waiting on the barrier fails its parity test;
+//   * mbarrier: arrival count + transaction bytes, phase parity, waits yield to the other threads.
+#pragma once
+
+#include <stdint.h>
+
+#include "simt_emu.hpp"
+
+namespace mspmv {
+
+struct EmuMbar {  // lives in the kernel's 8-byte mbarrier word
+    int64_t tx : 36;
+    uint64_t pending : 13;
+    uint64_t expected : 13;
+    uint64_t phase : 1;
+};
+static_assert(sizeof(EmuMbar) == 8, "mbarrier word");
+
+struct EmuBulkCopy {
+    void* dst;
+    const void* src;
+    uint32_t bytes;
+    uint64_t* bar;
+};
+inline std::vector<EmuBulkCopy>& emu_inflight()
+{
+    static std::vector<EmuBulkCopy> v;
+    return v;
+}
+inline EmuMbar* emu_bar(uint64_t* bar) { return reinterpret_cast<EmuMbar*>(bar); }
+
+inline void emu_mbar_check_complete(uint64_t* bar)
+{
+    EmuMbar* b = emu_bar(bar);
+    if (b->pending != 0 || b->tx != 0) return;
+    // the phase completes: the bulk copies that signal this barrier become visible now
+    auto& fl = emu_inflight();
+    for (size_t i = 0; i < fl.size();) {
+        if (fl[i].bar == bar) {
+            std::memcpy(fl[i].dst, fl[i].src, fl[i].bytes);
+            fl[i] = fl.back();
+            fl.pop_back();
+        } else {
+            ++i;
+        }
+    }
+    b->phase ^= 1;
+    b->pending = b->expected;
+    emu::S().progress = true;
+}
+
+inline void mbar_init(uint64_t* bar, int count)
+{
+    EmuMbar* b = emu_bar(bar);
+    b->tx = 0;
+    b->pending = (uint64_t)count;
+    b->expected = (uint64_t)count;
+    b->phase = 0;
+}
+inline void fence_mbar_init() {}
+inline void mbar_arrive(uint64_t* bar)
+{
+    EmuMbar* b = emu_bar(bar);
+    if (b->pending == 0) emu::die("mbarrier: more arrivals than expected");
+    b->pending -= 1;
+    emu_mbar_check_complete(bar);
+}
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    EmuMbar* b = emu_bar(bar);
+    b->tx += (int64_t)bytes;
+    mbar_arrive(bar);
+}
+inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) { return emu_bar(bar)->phase != (parity & 1u); }
+inline void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    emu::S().progress = true;
+    while (!mbar_test_wait(bar, parity)) emu::yield();
+}
+inline uint64_t l2_policy_evict_first() { return 0; }
+inline uint64_t l2_policy_evict_last() { return 0; }
+
+inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t)
+{
+    if (((uintptr_t)dst_smem & 15) || ((uintptr_t)src_gmem & 15) || (bytes & 15) || bytes == 0)
+        emu::die("cp.async.bulk: addresses must be 16-byte aligned and the size a non-zero multiple of 16");
+    std::memset(dst_smem, 0xCD, bytes);  // not visible before the barrier phase completes
+    emu_inflight().push_back(EmuBulkCopy{dst_smem, src_gmem, bytes, bar});
+    emu_bar(bar)->tx -= (int64_t)bytes;  // complete_tx
+    emu_mbar_check_complete(bar);
+}
+inline void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+    if (((uintptr_t)src_gmem & 15) || (bytes & 15) || bytes == 0)
+        emu::die("cp.async.bulk.prefetch: address must be 16-byte aligned and the size a non-zero multiple of 16");
+}
+inline void fence_proxy_async() {}
+inline void named_bar_sync(int id, int threads) { emu::block_barrier(id, threads); }
+
+#ifndef MSPMV_GATHER_FLAVOUR
+#define MSPMV_GATHER_FLAVOUR 5
+#endif
+template <typename T>
+inline T ld_gather(const T* p, uint64_t)
+{
+    return *p;
+}
+template <typename T>
+inline T ld_gather_l1(const T* p, uint64_t)
+{
+    return *p;
+}
+template <typename T>
+inline T ld_gather(const T* p)
+{
+    return *p;
+}
+
+}  // namespace mspmv

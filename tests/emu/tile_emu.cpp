@@ -1,0 +1,93 @@
+// tile_emu.cpp -- runs the tile engine's three kernels (merge-spmv_b200/csrc/spmv_tile.cuh, compiled
+// unchanged) under the host SIMT interpreter.  TEST INFRASTRUCTURE ONLY: built by
+// tests/test_kernel_emu.py, never part of the product.  The launch sequence mirrors
+// csrmv_launch() in merge-spmv_b200/csrc/mergespmv.cu (search -> tile -> carry fix-up).
+#define MSPMV_PTX_HEADER "ptx_emu.cuh"
+#include "simt_emu.hpp"
+
+#include "spmv_tile.cuh"
+
+#include <vector>
+
+namespace {
+
+using namespace mspmv;
+
+template <typename T>
+int shift_of(const void* p)
+{
+    return (int)((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
+}
+
+template <typename T, bool AXPBY>
+int run(const T* values, const int* row_offsets, const int* col, const T* x, T* y, int num_rows,
+        int num_nonzeros, T alpha, T beta, int prefetch_ahead, int* stats)
+{
+    using C = TileCfg<T>;
+    if (num_rows <= 0) return 0;
+    const int64_t merge_items = (int64_t)num_rows + num_nonzeros;
+    const int num_tiles = (int)((merge_items + C::TILE - 1) / C::TILE);
+    const int num_fix_blocks = (num_tiles + C::FIX - 1) / C::FIX;
+    // 16-byte aligned temporaries, uninitialised on purpose (the product's temp blob is)
+    std::vector<int4> coords_buf((size_t)(num_tiles + 1) / 2 + 2), cr_buf((size_t)num_tiles / 4 + 2),
+        c2r_buf((size_t)num_fix_blocks / 4 + 2);
+    std::vector<double> cv_buf((size_t)num_tiles + 2), c2v_buf((size_t)num_fix_blocks + 2);
+    int2* coords = reinterpret_cast<int2*>(coords_buf.data());
+    int* carry_rows = reinterpret_cast<int*>(cr_buf.data());
+    int* carry2_rows = reinterpret_cast<int*>(c2r_buf.data());
+    T* carry_vals = reinterpret_cast<T*>(cv_buf.data());
+    T* carry2_vals = reinterpret_cast<T*>(c2v_buf.data());
+    std::memset(coords_buf.data(), 0xEE, coords_buf.size() * sizeof(int4));
+    std::memset(cr_buf.data(), 0xEE, cr_buf.size() * sizeof(int4));
+    std::memset(cv_buf.data(), 0xEE, cv_buf.size() * sizeof(double));
+    unsigned int ticket = 0xEEEEEEEEu;
+
+    const int* row_end = row_offsets + 1;
+    emu::launch((unsigned)((num_tiles + 1 + 127) / 128), 128, [&] {
+        tile_search_kernel(row_end, num_rows, num_nonzeros, C::TILE, num_tiles, coords, &ticket);
+    });
+    emu::launch((unsigned)num_tiles, (unsigned)C::THREADS, [&] {
+        spmv_tile_kernel<T, AXPBY>(values, row_offsets, col, x, y, coords, carry_rows, carry_vals, alpha, beta,
+                                   num_rows, num_nonzeros, shift_of<T>(values), shift_of<int>(col),
+                                   shift_of<int>(row_offsets), prefetch_ahead);
+    });
+    if (num_tiles > 1) {
+        emu::launch((unsigned)num_fix_blocks, (unsigned)C::FIX, [&] {
+            carry_fixup_block_kernel<T, AXPBY>(carry_rows, carry_vals, num_tiles, num_rows, y, alpha, carry2_rows,
+                                               carry2_vals, &ticket);
+        });
+    }
+    if (stats) {
+        stats[0] = num_tiles;
+        stats[1] = C::TILE;
+        stats[2] = C::THREADS;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_csrmv_f64(const double* v, const int* ro, const int* ci, const double* x, double* y, int rows, int nnz,
+                  double alpha, double beta, int axpby, int prefetch_ahead, int* stats)
+{
+    return axpby ? run<double, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats)
+                 : run<double, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats);
+}
+int emu_csrmv_f32(const float* v, const int* ro, const int* ci, const float* x, float* y, int rows, int nnz,
+                  float alpha, float beta, int axpby, int prefetch_ahead, int* stats)
+{
+    return axpby ? run<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats)
+                 : run<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats);
+}
+
+// coordinates of arbitrary diagonals through the device search routine (merge_common.cuh)
+int emu_merge_path_search(const int* ro, int rows, int nnz, const int* diagonals, int n, int* coords)
+{
+    emu::launch((unsigned)((n + 127) / 128), 128, [&] {
+        diagonal_search_kernel(ro + 1, rows, nnz, diagonals, n, reinterpret_cast<int2*>(coords));
+    });
+    return 0;
+}
+}

@@ -1,0 +1,218 @@
+"""The tile engine's kernel *logic* on a box without a GPU.
+
+tests/emu/ holds a small host-side SIMT interpreter (coroutine per CUDA thread, warp collectives,
+mbarrier / cp.async.bulk contracts).  It compiles merge-spmv_b200/csrc/spmv_tile.cuh UNCHANGED with
+g++ -- only the inline-PTX wrappers of ptx_sm100.cuh are swapped for host stand-ins -- and runs the
+search / tile / carry fix-up kernels block by block.  This is test infrastructure: the library
+under test here is tests/emu/_build/libtile_emu.so, built by this file; the product
+(libmergespmv.so) contains no host path and still fails loudly without a GPU.  The parity tests
+proper are tests/test_gpu_parity.py (-m gpu).
+
+What it buys: bitmap / popcount-prefix / walk / segmented-scan / fix-up bugs, staging-range
+arithmetic (alignment contracts of cp.async.bulk are asserted), reads of staged data before the
+mbarrier wait (the destination is poisoned until the phase completes) and barrier deadlocks are
+caught by `pytest -m "not gpu"`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, random_csr
+
+EMU = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "merge-spmv_b200", "csrc")
+VARIANTS = {
+    # name -> extra -D flags (kernel variants that exist as compile-time switches in spmv_tile.cuh)
+    "shipped": [],
+    "prefix_shfl": ["-DMSPMV_PREFIX_SHFL"],
+    "ipt_11_15": ["-DMSPMV_TILE_IPT=(sizeof(T)==8?11:15)"],
+}
+
+
+def build(name):
+    out_dir = os.path.join(EMU, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libtile_emu_{name}.so")
+    srcs = [os.path.join(EMU, f) for f in ("tile_emu.cpp", "simt_emu.hpp", "ptx_emu.cuh")]
+    srcs += [os.path.join(CSRC, f) for f in ("spmv_tile.cuh", "merge_common.cuh", "tma_stage.cuh", "ptx_sm100.cuh")]
+    if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(s) for s in srcs + [__file__]):
+        return out
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fno-strict-aliasing", "-fno-gnu-unique", "-fPIC", "-shared", "-w",
+           "-I", EMU, "-I", CSRC, "-I", "/usr/local/cuda/include", *VARIANTS[name],
+           os.path.join(EMU, "tile_emu.cpp"), "-o", out]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+class Emu:
+    def __init__(self, name="shipped"):
+        self.lib = C.CDLL(build(name))
+        for sfx, fp in (("f64", C.c_double), ("f32", C.c_float)):
+            f = getattr(self.lib, f"emu_csrmv_{sfx}")
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p]
+        self.lib.emu_merge_path_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+
+    def csrmv(self, ro, col, val, x, y_in=None, alpha=1.0, beta=0.0, axpby=False, misalign=(0, 0, 0),
+              prefetch_ahead=0):
+        """misalign = element offsets (values, col, row_offsets) of the array bases from 16 bytes."""
+        dt = val.dtype
+        rows, nnz = ro.size - 1, int(ro[-1])
+
+        def place(a, k, dtype):  # copy `a` into a fresh buffer whose data starts k elements past 16-byte alignment
+            a = np.ascontiguousarray(a, dtype=dtype)
+            per16 = 16 // a.itemsize
+            buf = np.empty(a.size + 2 * per16 + 8, dtype=dtype)
+            base = (-(buf.ctypes.data // a.itemsize)) % per16  # first 16-byte aligned element
+            view = buf[base + k: base + k + a.size]
+            view[:] = a
+            assert (view.ctypes.data % 16) == (k * a.itemsize) % 16
+            return buf, view
+
+        keep = []
+        pv, v = place(val, misalign[0], dt)
+        pc, c = place(col, misalign[1], np.int32)
+        pr, r = place(ro, misalign[2], np.int32)
+        keep += [pv, pc, pr]
+        xx = np.ascontiguousarray(x, dtype=dt)
+        y = np.full(rows, np.nan, dtype=dt) if y_in is None else np.array(y_in, dtype=dt)
+        stats = np.zeros(4, np.int32)
+        fn = self.lib.emu_csrmv_f64 if dt == np.float64 else self.lib.emu_csrmv_f32
+        rc = fn(v.ctypes.data, r.ctypes.data, c.ctypes.data, xx.ctypes.data, y.ctypes.data, rows, nnz,
+                alpha, beta, int(axpby), prefetch_ahead, stats.ctypes.data)
+        assert rc == 0
+        self.stats = stats
+        return y
+
+    def search(self, ro, diags):
+        ro = np.ascontiguousarray(ro, np.int32)
+        d = np.ascontiguousarray(diags, np.int32)
+        out = np.zeros((d.size, 2), np.int32)
+        self.lib.emu_merge_path_search(ro.ctypes.data, ro.size - 1, int(ro[-1]), d.ctypes.data, d.size,
+                                       out.ctypes.data)
+        return out
+
+
+@pytest.fixture(scope="module", params=list(VARIANTS))
+def emu(request):
+    return Emu(request.param)
+
+
+@pytest.fixture(scope="module")
+def emu0():
+    return Emu("shipped")
+
+
+def tol_for(ro, dt):
+    lens = np.diff(ro).astype(np.float64)
+    return np.full(lens.shape, 1e-10) if dt == np.float64 else np.maximum(1e-6, 4 * np.sqrt(lens) * 2.0 ** -24)
+
+
+def assert_close(got, want, ro, dt, what=""):
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    bound = tol_for(ro, dt) * np.maximum(np.abs(want.astype(np.float64)), 1e-300)
+    bad = np.nonzero(~(err <= bound))[0]
+    assert bad.size == 0, f"{what}: {bad.size} rows out of tolerance, first {bad[:3]}, got {got[bad[:3]]} want {want[bad[:3]]}"
+
+
+SHAPES = [  # rows, cols, mean_len, empty_frac, long_rows
+    (1, 1, 1.0, 0.0, 0), (1, 50, 20, 0.0, 0), (2, 1, 0.6, 0.0, 0), (17, 1, 1.0, 0.3, 0),
+    (100, 64, 0.0, 1.0, 0),        # no nonzeros at all
+    (3000, 300, 0.05, 0.9, 0),     # almost all rows empty: > ROWCAP row ends per tile (row offsets read from global)
+    (1500, 2000, 9, 0.1, 2),       # a few long rows
+    (40, 30000, 700, 0.0, 2),      # rows spanning several tiles
+    (1, 40000, 30000, 0.0, 1),     # one huge row: > 256 tiles, second fix-up level
+    (9000, 128, 2, 0.5, 0),        # short rows
+    (1031, 1031, 31, 0.01, 0),
+]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_emu_random_structures_vs_oracle(emu, orc, dt):
+    rng = np.random.default_rng(2024)
+    for rows, cols, mean_len, empty, longs in SHAPES:
+        ro, col = random_csr(rng, rows, cols, mean_len, empty, longs)
+        nnz = int(ro[-1])
+        y = emu.csrmv(ro, col, np.ones(nnz, dt), np.ones(cols, dt))
+        assert np.array_equal(y, np.diff(ro).astype(dt)), (rows, cols, "exact-integer inputs must be bit-exact")
+        val = (0.5 + rng.random(nnz)).astype(dt)
+        x = (0.5 + rng.random(cols)).astype(dt)
+        want = orc.merge_csrmv(ro, col, val, x, num_threads=8)
+        got = emu.csrmv(ro, col, val, x)
+        assert_close(got, want, ro, dt, f"{rows}x{cols}")
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_emu_misaligned_bases(emu0, orc, dt):
+    """Array bases at every element offset inside a 16-byte granule (slices of larger arrays, as the
+    multi-GPU shards produce): the superset staging must stay inside the arrays and land every
+    element."""
+    rng = np.random.default_rng(5)
+    ro, col = random_csr(rng, 700, 900, 7, 0.2, 1)
+    nnz = int(ro[-1])
+    val = (0.5 + rng.random(nnz)).astype(dt)
+    x = (0.5 + rng.random(900)).astype(dt)
+    want = orc.merge_csrmv(ro, col, val, x, num_threads=3)
+    per16 = 16 // np.dtype(dt).itemsize
+    for kv in range(per16):
+        for kc in (0, 1, 3):
+            for kr in (0, 2, 3):
+                got = emu0.csrmv(ro, col, val, x, misalign=(kv, kc, kr))
+                assert_close(got, want, ro, dt, f"misalign {(kv, kc, kr)}")
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_emu_axpby_and_prefetch(emu0, orc, dt):
+    rng = np.random.default_rng(9)
+    ro, col = random_csr(rng, 2500, 1000, 6, 0.2, 1)
+    nnz = int(ro[-1])
+    val = (0.5 + rng.random(nnz)).astype(dt)
+    x = (0.5 + rng.random(1000)).astype(dt)
+    y0 = rng.random(2500).astype(dt)
+    ax = orc.merge_csrmv(ro, col, val, x, num_threads=4)
+    for alpha, beta in ((1.0, 0.0), (2.5, 0.0), (1.0, 1.0), (-0.75, 0.5)):
+        got = emu0.csrmv(ro, col, val, x, y_in=y0, alpha=alpha, beta=beta, axpby=True)
+        want = (dt(alpha) * ax + dt(beta) * y0).astype(dt)
+        err = np.abs(got - want)
+        scale = np.abs(dt(alpha) * ax) + np.abs(dt(beta) * y0)
+        assert np.all(err <= (1e-10 if dt == np.float64 else 3e-6) * scale), (alpha, beta)
+    # the optional L2 prefetch path (MSPMV_TILE_PREFETCH) is a pure hint; its ranges must be legal
+    got = emu0.csrmv(ro, col, val, x, prefetch_ahead=3)
+    assert_close(got, ax, ro, dt, "prefetch_ahead")
+
+
+def test_emu_known_answers(emu):
+    for dt in (np.float32, np.float64):
+        ro = np.array([0, 2, 2, 4, 8], np.int32)  # paper Fig. 8
+        val = np.array([1, 1, 3, 3, 4, 4, 4, 4], dt)
+        col = np.array([0, 2, 2, 3, 0, 1, 2, 3], np.int32)
+        assert emu.csrmv(ro, col, val, np.ones(4, dt)).tolist() == [2, 0, 6, 16]
+
+
+def test_emu_golden_vectors(emu0):
+    g = np.load(os.path.join(GOLDEN, "merge_csrmv_ref.npz"))
+    done = 0
+    for c in range(int(g["num_cases"])):
+        ro, col = g[f"c{c}_row_offsets"], g[f"c{c}_col"]
+        if ro.size - 1 + int(ro[-1]) > 400000:  # the interpreter runs ~1M merge items per second
+            continue
+        for tag, dt in (("f64", np.float64), ("f32", np.float32)):
+            got = emu0.csrmv(ro, col, g[f"c{c}_val_{tag}"], g[f"c{c}_x_{tag}"])
+            assert_close(got, g[f"c{c}_y_{tag}_p8"], ro, dt, f"golden case {c}")
+        assert np.array_equal(emu0.search(ro, g[f"c{c}_diags"]), g[f"c{c}_coords"]), f"golden coords case {c}"
+        done += 1
+    assert done >= 2
+
+
+def test_emu_deterministic(emu0):
+    rng = np.random.default_rng(11)
+    ro, col = random_csr(rng, 900, 5000, 40, 0.05, 2)
+    nnz = int(ro[-1])
+    val = rng.random(nnz).astype(np.float32)
+    x = rng.random(5000).astype(np.float32)
+    a = emu0.csrmv(ro, col, val, x)
+    b = emu0.csrmv(ro, col, val, x, misalign=(1, 2, 3))
+    assert np.array_equal(a, b), "same decomposition, same summation order: bits must not depend on alignment"
