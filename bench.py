@@ -241,6 +241,9 @@ def main():
     ap.add_argument("--cols", type=int, default=None, help="override the column count (x length) of the workload")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay each step (3 kernels, plus the collective and carry fold at N>1) as one CUDA graph; auto = on")
+    ap.add_argument("--gather-y", action="store_true",
+                    help="N>1: include the all_gather of the y slices in every step (solver-style: the whole y "
+                         "on every rank, ready to be the next x)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -295,14 +298,19 @@ def main():
     c0 = L.mspmv_launch_count()
     op(x)  # one eager step: also counts this library's kernels per step (graph replays bypass the counter)
     launches_per_step = L.mspmv_launch_count() - c0
-    step = op.capture(x) if use_graph else (lambda: op(x))
+    gather_y = bool(args.gather_y and world > 1)
+    if use_graph:
+        step = op.capture(x, gather_y=gather_y)
+    else:
+        step = (lambda: op.matvec_full(x)) if gather_y else (lambda: op(x))
 
     # ---- warm-up + correctness guard (exact identity on ones; finite on random) ----------------
     for _ in range(args.warmup):
         y = step()
     torch.cuda.synchronize()
     if args.values == "ones":
-        lens = torch.diff(torch.from_numpy(ro_np[shard.x0: shard.x1 + 1])).to(dt).to(dev)
+        lo, hi = (0, rows) if gather_y else (shard.x0, shard.x1)
+        lens = torch.diff(torch.from_numpy(ro_np[lo: hi + 1])).to(dt).to(dev)
         assert torch.equal(y, lens), "warm-up result is not the row-length vector"
     else:
         assert bool(torch.isfinite(y).all())
@@ -349,6 +357,16 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tile_kernel" if (args.engine or "tile") != "stream" else "spmv_stream_kernel",
                 "algorithmic_bytes_per_launch": shard_bytes,
                 "note": "duration = whole step (search + tile + carry fix-up kernels; the tile kernel is 94.7% of it, profiles/launches_r01.csv), CUDA events"}
+
+    if kind in ("uniform", "powerlaw"):
+        # Random columns: every nonzero costs one 32-byte L2->L1 sector of x, and one SM retires
+        # ~0.93 such L1-miss sectors per clock (profiles/microbench_r01.txt: 270 G gathers/s chip-wide
+        # for any L2-resident table, fp32 == fp64).  That, not HBM, is the binding limit of these
+        # workloads; reported beside the HBM roofline so frac can be read against the right ceiling.
+        g_rate = shard.nnz / (ms_per_step * 1e-3) / 1e9
+        roofline["secondary"] = {"bound": "l1tex gather sectors (random x[col])", "achieved": g_rate,
+                                 "peak": 270.0, "unit": "G gathers/s", "frac": g_rate / 270.0,
+                                 "peak_source": "profiles/microbench_r01.txt (measured on this pool's B200)"}
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------
     e2e = None
@@ -417,7 +435,7 @@ def main():
                            kind, "stratified-uniform over all columns, sorted, distinct"),
                        "parallelism": f"merge-path shards x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
-                       "engine": args.engine or "tile", "cuda_graph": use_graph},
+                       "engine": args.engine or "tile", "cuda_graph": use_graph, "gather_y": gather_y},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "hbm_gbs_algorithmic": achieved * (1 if world == 1 else world),

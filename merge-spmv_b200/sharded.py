@@ -125,28 +125,36 @@ class ShardedSpmv:
         self.shard = shard
         self.group = group
         dev = shard.val.device
-        self.y_local = torch.zeros(shard.local_rows, dtype=shard.val.dtype, device=dev)
+        # y slices have different lengths (equal WORK per rank, not equal rows): the exchange of y
+        # (gather_y) sends fixed-size records of `pad` rows, so the local result lives at the head
+        # of a buffer of at least that size and is sent in place.
+        self._sizes = [int(shard.coords[g + 1, 0] - shard.coords[g, 0]) for g in range(shard.world)]
+        self._pad = max(max(self._sizes), 1)
+        self._ybuf = torch.zeros(max(shard.local_rows, self._pad), dtype=shard.val.dtype, device=dev)
+        self.y_local = self._ybuf[:shard.local_rows]
         self.carries = torch.zeros(shard.world, dtype=shard.val.dtype, device=dev)
+        self._gathered = None  # (world, pad) receive buffer of gather_y, allocated on first use
         # injectable for the CPU (gloo) tests of the exchange logic; the defaults are the CUDA path
         self._local_spmv = local_spmv or (lambda s, x, y: csrmv(s.row_offsets, s.col, s.val, x, y,
                                                                num_cols=s.cols))
         self._fold = fold or apply_carries
 
-    def capture(self, x):
-        """Record one whole step (search + tile + fix-up kernels, the all_gather, the carry fold) into
-        a CUDA graph over the fixed input buffer ``x``; returns a callable that replays it with a
-        single launch.  Removes per-kernel launch gaps and the host cost of the collective."""
+    def capture(self, x, gather_y=False):
+        """Record one whole step (search + tile + fix-up kernels, the all_gather, the carry fold --
+        and, with ``gather_y``, the exchange of the y slices) into a CUDA graph over the fixed
+        input buffer ``x``; returns a callable that replays it with a single launch.  Removes
+        per-kernel launch gaps and the host cost of the collectives."""
+        step = self.matvec_full if gather_y else self
         side = torch.cuda.Stream(device=self.y_local.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):  # warm-up outside capture: one-time attribute setup, NCCL channels
-                self(x)
+                step(x)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self(x)
-        out = self.y_local[:self.shard.owned_rows]
+            out = step(x)
 
         def replay():
             graph.replay()
@@ -154,6 +162,33 @@ class ShardedSpmv:
 
         replay.graph = graph
         return replay
+
+    def gather_y(self, out=None):
+        """The step on the far side of the path for iterative solvers: after a
+        product every rank holds only its rows of y, but the next product needs the whole vector
+        as x.  ONE ``all_gather`` of fixed-size records (``pad`` = longest slice) taken in place
+        from the local result, then ``world`` contiguous copies drop the padding.  Call
+        collectively, after ``self(x)``.  Returns the full y (length ``rows_global``)."""
+        s = self.shard
+        dt, dev = self.y_local.dtype, self.y_local.device
+        if out is None:
+            out = torch.empty(s.rows_global, dtype=dt, device=dev)
+        if s.world == 1:
+            out.copy_(self.y_local[:s.owned_rows])
+            return out
+        if self._gathered is None:
+            self._gathered = torch.empty(s.world * self._pad, dtype=dt, device=dev)
+        dist.all_gather_into_tensor(self._gathered, self._ybuf[:self._pad], group=self.group)
+        for g, n in enumerate(self._sizes):
+            if n:
+                x_g = int(s.coords[g, 0])
+                out[x_g:x_g + n].copy_(self._gathered[g * self._pad:g * self._pad + n])
+        return out
+
+    def matvec_full(self, x, out=None):
+        """``y = A x`` replicated on every rank: the sharded product followed by ``gather_y``."""
+        self(x)
+        return self.gather_y(out)
 
     def __call__(self, x):
         s = self.shard

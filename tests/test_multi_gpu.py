@@ -50,10 +50,18 @@ def _worker(rank, world, port, dtype_name, out_dir):
     lens = np.diff(ro)[shard.x0:shard.x1].astype(np.float64)
     tol = 1e-10 if dt == torch.float64 else np.maximum(1e-6, 4 * np.sqrt(lens) * 2.0 ** -24)
     ok_oracle = bool(np.all(np.abs(got - want) <= tol * np.abs(want)))
-    flag = torch.tensor([int(ok_local and ok_oracle)], device=dev)
+    # the y exchange (every rank gets the whole vector), eagerly and replayed from a CUDA graph
+    rtol = 1e-5 if dt == torch.float32 else 1e-12
+    ok_full = torch.allclose(op.matvec_full(x), full, rtol=rtol, atol=0)
+    replay = op.capture(x, gather_y=True)
+    ok_full = ok_full and torch.allclose(replay(), full, rtol=rtol, atol=0)
+    torch.cuda.synchronize()
+    flag = torch.tensor([int(ok_local and ok_oracle and ok_full)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         np.save(os.path.join(out_dir, f"ok_{dtype_name}.npy"), np.array([int(flag.item())]))
+    del replay  # a captured graph holds NCCL work: release it before the communicator
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 

@@ -60,11 +60,22 @@ def _worker(rank, world, port, dtype_name, out_dir):
     mine[:y_own.numel()] = y_own
     pieces = [torch.empty(pad, dtype=dt) for _ in sizes]
     dist.all_gather(pieces, mine)
+    want = orc.merge_csrmv(ro, col, val, x.numpy(), world)
+    got = torch.cat([p[:n] for p, n in zip(pieces, sizes)]).numpy()
+
+    # the exchange on the far side of the path (solver-style ping-pong): every rank gets the whole y
+    # from ONE all_gather of padded slices, feeds it back as the next x
+    y_full = op.matvec_full(x).clone()
+    ok_full = np.array_equal(y_full.numpy(), want)
+    x2 = y_full / y_full.abs().max()
+    y2 = op.matvec_full(x2)
+    want2 = orc.merge_csrmv(ro, col, val, x2.numpy(), world)
+    ok_chain = np.array_equal(y2.numpy(), want2)
+    flag = torch.tensor([int(ok_full and ok_chain)])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        got = torch.cat([p[:n] for p, n in zip(pieces, sizes)]).numpy()
-        want = orc.merge_csrmv(ro, col, val, x.numpy(), world)
         np.save(os.path.join(out_dir, f"ok_{dtype_name}_{world}.npy"),
-                np.array([np.array_equal(got, want), got.size]))
+                np.array([np.array_equal(got, want), got.size, int(flag.item())]))
     dist.destroy_process_group()
 
 
@@ -76,3 +87,4 @@ def test_sharded_spmv_gloo(tmp_path, world, dtype_name):
     res = np.load(tmp_path / f"ok_{dtype_name}_{world}.npy")
     assert res[0] == 1, "sharded result differs from the oracle with p = world threads"
     assert res[1] == 10000
+    assert res[2] == 1, "gather_y / matvec_full (replicated y, fed back as x) differs from the oracle on some rank"
