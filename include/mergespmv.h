@@ -166,10 +166,19 @@ uint64_t mspmv_launch_count(void);
  * out[4] = kernels per call. */
 int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out);
 const char* mspmv_error_string(int err);
-/* Test hook: pick the kernel engine for subsequent calls in this process: "stream" (persistent
- * TMA-fed swaths, the default), "tile" (one threadblock per tile + search kernel) or "auto".
- * Also settable with the MSPMV_ENGINE environment variable.  Returns 0, or 1 for a bad name. */
+/* Test hook: pick the kernel engine for subsequent calls in this process: "tile" (one threadblock
+ * per tile + search kernel; what "auto", the default, selects) or "stream" (persistent TMA-fed
+ * swaths, kept as a test subject).  Also settable with the MSPMV_ENGINE environment variable.
+ * Returns 0, or 1 for a bad name. */
 int mspmv_set_engine(const char* name);
+/* Tuning options of the tile engine for subsequent calls in this process.  Returns 0, or 1 for an
+ * unknown name.
+ *   "small_fused_tiles"  n > 0: matrices of at most n tiles run as ONE launch (each block searches
+ *                        its own merge-path coordinates, the last block to finish folds the
+ *                        carries) instead of search + tile + fix-up kernels -- the small-matrix
+ *                        overhead the paper names (section IV.B; dispatch_spmv_orig.cuh:674-679).
+ *                        0: off (default).  -1: back to the MSPMV_SMALL_FUSED environment value. */
+int mspmv_set_option(const char* name, int value);
 
 #ifdef __cplusplus
 }

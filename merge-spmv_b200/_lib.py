@@ -33,6 +33,7 @@ SIGNATURES = {
     "mspmv_csrmv_config": (_i, [_i, _i, _i, C.POINTER(_i)]),
     "mspmv_error_string": (C.c_char_p, [_i]),
     "mspmv_set_engine": (_i, [C.c_char_p]),
+    "mspmv_set_option": (_i, [C.c_char_p, _i]),
 }
 
 

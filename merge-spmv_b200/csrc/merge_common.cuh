@@ -55,6 +55,34 @@ __device__ __forceinline__ int2 merge_path_search_global(int64_t diag64, const i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-cooperative 32-ary merge-path search in global memory: ~log33(range) dependent loads
+// instead of log2(range).  Same unique answer as merge_path_search().
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int2 warp_merge_path_search_global(int64_t diag64,
+                                                              const int* __restrict__ row_end_offsets,
+                                                              int num_rows, int num_nonzeros, int lane)
+{
+    int64_t total = (int64_t)num_rows + num_nonzeros;
+    int diag = (int)(diag64 < total ? diag64 : total);
+    int lo = max(diag - num_nonzeros, 0);
+    int hi = min(diag, num_rows);
+    while (lo < hi) {
+        int span = hi - lo;
+        // 32 pivots strictly inside [lo, hi); duplicates are fine for tiny spans
+        int pivot = lo + (int)(((int64_t)span * (lane + 1)) / 33);
+        pivot = min(pivot, hi - 1);
+        bool go_up = __ldg(row_end_offsets + pivot) <= diag - pivot - 1;  // predicate is monotone in pivot
+        unsigned up = __ballot_sync(kFull, go_up);
+        int n_up = __popc(up);
+        int new_lo = n_up > 0 ? __shfl_sync(kFull, pivot, n_up - 1) + 1 : lo;
+        int new_hi = n_up < 32 ? __shfl_sync(kFull, pivot, n_up) : hi;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    return make_int2(min(lo, num_rows), diag - lo);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Segmented (reduce-by-key) scan element: `ended` = a row end occurred at or after the segment
 // start, `val` = partial sum since the last row end.  combine(a, b) with a earlier than b is
 // ReduceByKeyOp (thread_operators.cuh:290-300) specialised to "key changed" flags.

@@ -75,6 +75,21 @@ static Engine engine_from_env()
 #define MSPMV_TILE_PREFETCH_DEFAULT 0  // 0 = off (shipped); -1 = sm_count * 11
 #endif
 
+// Single-launch path for small matrices (spmv_tile_fused_kernel): used when the tile count is at
+// most this threshold.  0 = off (shipped default until it has been timed on the GPU);
+// MSPMV_SMALL_FUSED=<tiles> or mspmv_set_option("small_fused_tiles", n) turn it on.
+static std::atomic<int> g_small_fused_tiles{-1};
+static int small_fused_tiles()
+{
+    int v = g_small_fused_tiles.load(std::memory_order_relaxed);
+    if (v >= 0) return v;
+    static int env = [] {
+        const char* e = std::getenv("MSPMV_SMALL_FUSED");
+        return e ? std::atoi(e) : 0;
+    }();
+    return env > 0 ? env : 0;
+}
+
 static inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 
 template <typename T>
@@ -179,15 +194,30 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     int* carry2_rows = reinterpret_cast<int*>(temp + p.off_carry2_rows);
     T* carry2_vals = reinterpret_cast<T*>(temp + p.off_carry2_vals);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(temp + p.off_ticket);
+    const int shift_v = (int)((reinterpret_cast<uintptr_t>(values) & 15) / sizeof(T));
+    const int shift_c = (int)((reinterpret_cast<uintptr_t>(col) & 15) / sizeof(int));
+    const int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
+    dim3 grid(p.num_tiles), block(C::THREADS);
+    if (p.num_tiles <= small_fused_tiles()) {
+        // one launch: every block searches its own coordinates, the last block folds the carries
+        static bool fused_configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!fused_configured[dev & 63]) {
+            cudaFuncSetAttribute(spmv_tile_fused_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, 70);
+            fused_configured[dev & 63] = true;
+        }
+        if (p.num_tiles > 1) MSPMV_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
+        spmv_tile_fused_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, carry_rows,
+                                                                    carry_vals, alpha, beta, num_rows, num_nonzeros,
+                                                                    shift_v, shift_c, shift_r, ticket);
+        return post_launch("spmv_tile_fused_kernel", grid, block, 0, stream, debug_sync);
+    }
     dim3 sgrid((p.num_tiles + 1 + 127) / 128), sblock(128);
     tile_search_kernel<<<sgrid, sblock, 0, stream>>>(row_end, num_rows, num_nonzeros, C::TILE, p.num_tiles,
                                                      coords, ticket);
     int rc = post_launch("tile_search_kernel", sgrid, sblock, 0, stream, debug_sync);
     if (rc) return rc;
-    const int shift_v = (int)((reinterpret_cast<uintptr_t>(values) & 15) / sizeof(T));
-    const int shift_c = (int)((reinterpret_cast<uintptr_t>(col) & 15) / sizeof(int));
-    const int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
-    dim3 grid(p.num_tiles), block(C::THREADS);
     {
         // Shared-memory carve-out: the x gathers need L1 capacity for their misses in flight
         // (gather throughput halves once shared memory takes > ~160 KB of the 228 KB, see
@@ -593,7 +623,7 @@ int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out
             out[1] = TileCfg<T>::THREADS;
             out[2] = TileCfg<T>::TILE;
             out[3] = 0;
-            out[4] = p.num_tiles > 1 ? 3 : 2;
+            out[4] = p.num_tiles <= small_fused_tiles() ? 1 : (p.num_tiles > 1 ? 3 : 2);
         }
         return 0;
     };
@@ -610,6 +640,16 @@ int mspmv_set_engine(const char* name)
     else if (!std::strcmp(name, "stream")) g_engine_override = (int)Engine::Stream;
     else return 1;
     return 0;
+}
+
+int mspmv_set_option(const char* name, int value)
+{
+    if (!name) return 1;
+    if (!std::strcmp(name, "small_fused_tiles")) {
+        g_small_fused_tiles = value < 0 ? -1 : value;  // -1: back to the environment / default
+        return 0;
+    }
+    return 1;
 }
 
 }  // extern "C"

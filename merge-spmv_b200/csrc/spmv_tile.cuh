@@ -81,11 +81,15 @@ __global__ void diagonal_search_kernel(const int* __restrict__ row_end_offsets, 
 }
 
 // ---- step 2: one tile per threadblock
+// tile_body: everything a block does with its tile once the tile's start / end coordinates (c0, c1)
+// are known.  Shared by the three-launch path (coordinates from tile_search_kernel) and the
+// single-launch path for small matrices (coordinates searched by the block itself).
 template <typename T, bool AXPBY>
-__global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
+__device__ __forceinline__ void tile_body(
     const T* __restrict__ values, const int* __restrict__ row_offsets,
     const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
-    const int2* __restrict__ coords, int* __restrict__ carry_rows, T* __restrict__ carry_vals, T alpha,
+    const int2* __restrict__ coords, const int tid, const int tile, const int2 c0, const int2 c1,
+    int* __restrict__ carry_rows, T* __restrict__ carry_vals, T alpha,
     T beta, int num_rows, int num_nonzeros, int shift_v, int shift_c, int shift_r, int prefetch_ahead)
 {
     using C = TileCfg<T>;
@@ -99,11 +103,7 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     alignas(16) __shared__ Seg<T> s_warp[NW];
     alignas(8) __shared__ uint64_t s_bar;
 
-    const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
-    const int2 c0 = __ldg(coords + tile);
-    const int2 c1 = __ldg(coords + tile + 1);
     const int x0 = c0.x, y0 = c0.y;
     const int nrows = c1.x - c0.x;           // rows that end in this tile
     const int nnzs = c1.y - c0.y;
@@ -280,6 +280,88 @@ __global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
     if (tid == 0) {
         carry_rows[tile] = c1.x;
         carry_vals[tile] = total.val;
+    }
+}
+
+template <typename T, bool AXPBY>
+__global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_kernel(
+    const T* __restrict__ values, const int* __restrict__ row_offsets,
+    const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
+    const int2* __restrict__ coords, int* __restrict__ carry_rows, T* __restrict__ carry_vals, T alpha,
+    T beta, int num_rows, int num_nonzeros, int shift_v, int shift_c, int shift_r, int prefetch_ahead)
+{
+    const int tid = threadIdx.x;  // read here: the launch bound gives the compiler its range
+    const int tile = blockIdx.x;
+    const int2 c0 = __ldg(coords + tile);
+    const int2 c1 = __ldg(coords + tile + 1);
+    tile_body<T, AXPBY>(values, row_offsets, column_indices, x, y, coords, tid, tile, c0, c1, carry_rows, carry_vals,
+                        alpha, beta, num_rows, num_nonzeros, shift_v, shift_c, shift_r, prefetch_ahead);
+}
+
+// ---- single-launch path for small matrices -------------------------------------------------------
+// The paper (section IV.B) and the reference (dispatch_spmv_orig.cuh:674-679: the search kernel is
+// skipped when there are fewer tiles than SMs can hide) name the extra launches as the small-matrix
+// overhead.  Here a matrix of at most a few thousand tiles runs in ONE launch:
+//   * warps 0 and 1 find the block's start / end coordinate themselves with the warp-cooperative
+//     32-ary MergePathSearch (4 dependent L2 round trips instead of ~20);
+//   * tile_body as usual;
+//   * the last block to finish (ticket counter, zeroed by a 4-byte memset node in front of the
+//     launch) folds ALL carries into y with a block-wide segmented scan, 128 at a time, in carry
+//     order -- runs of equal rows are summed left to right and added to y once, the order of the
+//     CPU loop cpu_spmv.cpp:348-352; carries with row >= num_rows are dropped.
+// Other blocks' y stores and carries are visible to the last block: every block fences before
+// taking its ticket, and the last block's second fence invalidates its L1 (SASS CCTL.IVALL).
+template <typename T, bool AXPBY>
+__global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile_fused_kernel(
+    const T* __restrict__ values, const int* __restrict__ row_offsets,
+    const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
+    int* __restrict__ carry_rows, T* __restrict__ carry_vals, T alpha, T beta, int num_rows,
+    int num_nonzeros, int shift_v, int shift_c, int shift_r, unsigned int* __restrict__ ticket)
+{
+    using C = TileCfg<T>;
+    constexpr int NW = C::THREADS / 32;
+    __shared__ int2 s_coord[2];
+    __shared__ bool s_last;
+    alignas(16) __shared__ Seg<T> s_fix[NW];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    if (warp < 2) {
+        const int2 c = warp_merge_path_search_global((int64_t)(tile + warp) * C::TILE, row_offsets + 1, num_rows,
+                                                     num_nonzeros, lane);
+        if (lane == 0) s_coord[warp] = c;
+    }
+    __syncthreads();
+    const int2 c0 = s_coord[0], c1 = s_coord[1];
+    tile_body<T, AXPBY>(values, row_offsets, column_indices, x, y, nullptr, tid, tile, c0, c1, carry_rows, carry_vals,
+                        alpha, beta, num_rows, num_nonzeros, shift_v, shift_c, shift_r, 0);
+    const int n = gridDim.x;
+    if (n == 1) return;  // a single tile has no carry to fold (dispatch_spmv_orig.cuh:721)
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)n - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+
+    Seg<T> carry;  // the run that touches the end of the previous chunk
+    carry.val = T(0);
+    carry.ended = 0;
+    for (int base = 0; base < n; base += C::THREADS) {
+        const int i = base + tid;
+        const int row = i < n ? carry_rows[i] : INT_MAX;
+        const int prev_row = (i > 0 && i < n) ? carry_rows[i - 1] : -1;
+        const int next_row = i + 1 < n ? carry_rows[i + 1] : INT_MAX;
+        Seg<T> e, excl, total;
+        e.val = i < n ? carry_vals[i] : T(0);
+        e.ended = row != prev_row;  // a new run starts here
+        block_seg_scan_exclusive<T, NW>(e, carry, s_fix, tid, 1, excl, total);
+        const T run_sum = e.ended ? e.val : excl.val + e.val;  // my run up to and including me
+        if (i < n && row != next_row && row < num_rows) y[row] += AXPBY ? alpha * run_sum : run_sum;
+        carry.val = total.val;
+        carry.ended = 0;
+        __syncthreads();  // s_fix is reused by the next chunk
     }
 }
 

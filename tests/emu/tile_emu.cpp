@@ -21,7 +21,7 @@ int shift_of(const void* p)
 
 template <typename T, bool AXPBY>
 int run(const T* values, const int* row_offsets, const int* col, const T* x, T* y, int num_rows,
-        int num_nonzeros, T alpha, T beta, int prefetch_ahead, int* stats)
+        int num_nonzeros, T alpha, T beta, int prefetch_ahead, int* stats, bool fused = false)
 {
     using C = TileCfg<T>;
     if (num_rows <= 0) return 0;
@@ -43,6 +43,20 @@ int run(const T* values, const int* row_offsets, const int* col, const T* x, T* 
     unsigned int ticket = 0xEEEEEEEEu;
 
     const int* row_end = row_offsets + 1;
+    if (stats) {
+        stats[0] = num_tiles;
+        stats[1] = C::TILE;
+        stats[2] = C::THREADS;
+    }
+    if (fused) {  // single-launch path for small matrices (cudaMemsetAsync of the ticket + one kernel)
+        ticket = 0u;
+        emu::launch((unsigned)num_tiles, (unsigned)C::THREADS, [&] {
+            spmv_tile_fused_kernel<T, AXPBY>(values, row_offsets, col, x, y, carry_rows, carry_vals, alpha, beta,
+                                             num_rows, num_nonzeros, shift_of<T>(values), shift_of<int>(col),
+                                             shift_of<int>(row_offsets), &ticket);
+        });
+        return 0;
+    }
     emu::launch((unsigned)((num_tiles + 1 + 127) / 128), 128, [&] {
         tile_search_kernel(row_end, num_rows, num_nonzeros, C::TILE, num_tiles, coords, &ticket);
     });
@@ -56,11 +70,6 @@ int run(const T* values, const int* row_offsets, const int* col, const T* x, T* 
             carry_fixup_block_kernel<T, AXPBY>(carry_rows, carry_vals, num_tiles, num_rows, y, alpha, carry2_rows,
                                                carry2_vals, &ticket);
         });
-    }
-    if (stats) {
-        stats[0] = num_tiles;
-        stats[1] = C::TILE;
-        stats[2] = C::THREADS;
     }
     return 0;
 }
@@ -80,6 +89,19 @@ int emu_csrmv_f32(const float* v, const int* ro, const int* ci, const float* x, 
 {
     return axpby ? run<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats)
                  : run<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats);
+}
+
+int emu_csrmv_fused_f64(const double* v, const int* ro, const int* ci, const double* x, double* y, int rows, int nnz,
+                        double alpha, double beta, int axpby, int prefetch_ahead, int* stats)
+{
+    return axpby ? run<double, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, true)
+                 : run<double, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, true);
+}
+int emu_csrmv_fused_f32(const float* v, const int* ro, const int* ci, const float* x, float* y, int rows, int nnz,
+                        float alpha, float beta, int axpby, int prefetch_ahead, int* stats)
+{
+    return axpby ? run<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, true)
+                 : run<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, true);
 }
 
 // coordinates of arbitrary diagonals through the device search routine (merge_common.cuh)

@@ -51,13 +51,14 @@ class Emu:
     def __init__(self, name="shipped"):
         self.lib = C.CDLL(build(name))
         for sfx, fp in (("f64", C.c_double), ("f32", C.c_float)):
-            f = getattr(self.lib, f"emu_csrmv_{sfx}")
-            f.restype = C.c_int
-            f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p]
+            for stem in ("emu_csrmv_", "emu_csrmv_fused_"):
+                f = getattr(self.lib, stem + sfx)
+                f.restype = C.c_int
+                f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p]
         self.lib.emu_merge_path_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
 
     def csrmv(self, ro, col, val, x, y_in=None, alpha=1.0, beta=0.0, axpby=False, misalign=(0, 0, 0),
-              prefetch_ahead=0):
+              prefetch_ahead=0, fused=False):
         """misalign = element offsets (values, col, row_offsets) of the array bases from 16 bytes."""
         dt = val.dtype
         rows, nnz = ro.size - 1, int(ro[-1])
@@ -80,7 +81,7 @@ class Emu:
         xx = np.ascontiguousarray(x, dtype=dt)
         y = np.full(rows, np.nan, dtype=dt) if y_in is None else np.array(y_in, dtype=dt)
         stats = np.zeros(4, np.int32)
-        fn = self.lib.emu_csrmv_f64 if dt == np.float64 else self.lib.emu_csrmv_f32
+        fn = getattr(self.lib, ("emu_csrmv_fused_" if fused else "emu_csrmv_") + ("f64" if dt == np.float64 else "f32"))
         rc = fn(v.ctypes.data, r.ctypes.data, c.ctypes.data, xx.ctypes.data, y.ctypes.data, rows, nnz,
                 alpha, beta, int(axpby), prefetch_ahead, stats.ctypes.data)
         assert rc == 0
@@ -216,3 +217,30 @@ def test_emu_deterministic(emu0):
     a = emu0.csrmv(ro, col, val, x)
     b = emu0.csrmv(ro, col, val, x, misalign=(1, 2, 3))
     assert np.array_equal(a, b), "same decomposition, same summation order: bits must not depend on alignment"
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_emu_fused_single_launch(emu0, orc, dt):
+    """The single-launch path for small matrices (mspmv_set_option("small_fused_tiles", n)): every
+    block searches its own coordinates, the last block folds all carries with a chunked segmented
+    scan.  Same tiles and carries as the three-launch path."""
+    rng = np.random.default_rng(77)
+    for rows, cols, mean_len, empty, longs in SHAPES:
+        ro, col = random_csr(rng, rows, cols, mean_len, empty, longs)
+        nnz = int(ro[-1])
+        y = emu0.csrmv(ro, col, np.ones(nnz, dt), np.ones(cols, dt), fused=True)
+        assert np.array_equal(y, np.diff(ro).astype(dt)), (rows, cols, "exact-integer inputs must be bit-exact")
+        val = (0.5 + rng.random(nnz)).astype(dt)
+        x = (0.5 + rng.random(cols)).astype(dt)
+        got = emu0.csrmv(ro, col, val, x, fused=True)
+        assert_close(got, orc.merge_csrmv(ro, col, val, x, num_threads=8), ro, dt, f"{rows}x{cols}")
+    # alpha / beta through the fused path
+    ro, col = random_csr(rng, 900, 400, 5, 0.2, 1)
+    nnz = int(ro[-1])
+    val = (0.5 + rng.random(nnz)).astype(dt)
+    x = (0.5 + rng.random(400)).astype(dt)
+    y0 = rng.random(900).astype(dt)
+    ax = orc.merge_csrmv(ro, col, val, x, num_threads=4)
+    got = emu0.csrmv(ro, col, val, x, y_in=y0, alpha=-0.75, beta=0.5, axpby=True, fused=True)
+    want = (dt(-0.75) * ax + dt(0.5) * y0).astype(dt)
+    assert np.all(np.abs(got - want) <= (1e-10 if dt == np.float64 else 3e-6) * (np.abs(0.75 * ax) + np.abs(0.5 * y0)))

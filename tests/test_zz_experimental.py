@@ -1,0 +1,94 @@
+"""GPU parity of the opt-in variants that have NOT been timed on a B200 yet (they were written in a
+session without GPU minutes; their kernel logic is covered on CPU by tests/test_kernel_emu.py).
+They are off by default in the library, so these tests are off by default too:
+
+    MSPMV_TEST_EXPERIMENTAL=1 python -m pytest tests/test_zz_experimental.py -m gpu -q
+
+The file sorts last so that `pytest -x` reaches it only after the shipped path has passed.
+Current subjects:
+  * small_fused_tiles  -- the single-launch path for small matrices (spmv_tile_fused_kernel).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_csr
+
+import merge_spmv_b200 as ms
+from merge_spmv_b200.csrmv import csrmv_config
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MSPMV_TEST_EXPERIMENTAL") != "1",
+                                 reason="opt-in variants: set MSPMV_TEST_EXPERIMENTAL=1")]
+
+DEV = "cuda:0"
+
+
+@pytest.fixture
+def fused():
+    assert ms.lib().mspmv_set_option(b"small_fused_tiles", 1 << 20) == 0
+    yield
+    assert ms.lib().mspmv_set_option(b"small_fused_tiles", -1) == 0
+
+
+def gpu_csrmv(ro, col, val, x, **kw):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    y = ms.csrmv(t(ro), t(col), t(val), t(x), **kw)
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+def tol_for(ro, dt):
+    lens = np.diff(ro).astype(np.float64)
+    return np.full(lens.shape, 1e-10) if np.dtype(dt) == np.float64 else np.maximum(1e-6, 4 * np.sqrt(lens) * 2.0 ** -24)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_fused_vs_oracle_and_three_launch(orc, fused, dt):
+    rng = np.random.default_rng(303)
+    shapes = [(1, 1, 1.0, 0.0, 0), (1, 50, 20, 0.0, 0), (17, 1, 1.0, 0.3, 0), (100, 64, 0.0, 1.0, 0),
+              (5000, 300, 0.05, 0.9, 0), (3000, 4000, 9, 0.1, 2), (257, 100000, 700, 0.0, 3),
+              (20000, 20000, 3, 0.3, 1), (1, 200000, 150000, 0.0, 1), (70000, 128, 2, 0.5, 0),
+              (16384, 16384, 32, 0.0, 0)]  # the last one is BASELINE config 1
+    for rows, cols, mean_len, empty, longs in shapes:
+        ro, col = random_csr(rng, rows, cols, mean_len, empty, longs)
+        nnz = int(ro[-1])
+        assert csrmv_config(np.dtype(dt).itemsize, rows, nnz)["kernels_per_call"] == 1
+        y = gpu_csrmv(ro, col, np.ones(nnz, dt), np.ones(cols, dt))
+        assert np.array_equal(y, np.diff(ro).astype(dt)), (rows, cols, "exact")
+        val = (0.5 + rng.random(nnz)).astype(dt)
+        x = (0.5 + rng.random(cols)).astype(dt)
+        want = orc.merge_csrmv(ro, col, val, x, num_threads=8)
+        got = gpu_csrmv(ro, col, val, x)
+        err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        assert np.all(err <= tol_for(ro, dt) * np.maximum(np.abs(want), 1e-300)), (rows, cols)
+        # twice: same bits (deterministic fold)
+        assert np.array_equal(got, gpu_csrmv(ro, col, val, x))
+        y0 = (0.5 + rng.random(rows)).astype(dt)
+        got_ab = gpu_csrmv(ro, col, val, x, y=torch.from_numpy(y0).to(DEV), alpha=2.0, beta=-1.0)
+        ref = 2.0 * want.astype(np.float64) - y0.astype(np.float64)
+        scale = 2.0 * np.abs(want.astype(np.float64)) + np.abs(y0.astype(np.float64))
+        assert np.all(np.abs(got_ab - ref) <= 4 * tol_for(ro, dt) * scale), (rows, cols, "alpha/beta")
+
+
+def test_fused_in_cuda_graph(fused):
+    """The ticket memset is a graph node: capture once, replay many, same result every time."""
+    rng = np.random.default_rng(5)
+    ro, col = random_csr(rng, 16384, 16384, 32, 0.0, 0)
+    nnz = int(ro[-1])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    rod, cold, vald, xd = t(ro), t(col), t((0.5 + rng.random(nnz))), t(0.5 + rng.random(16384))
+    y = torch.empty(16384, dtype=torch.float64, device=DEV)
+    ms.csrmv(rod, cold, vald, xd, y)  # warm (temp blob, attributes)
+    torch.cuda.synchronize()
+    first = y.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ms.csrmv(rod, cold, vald, xd, y)
+    for _ in range(5):
+        y.fill_(float("nan"))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y, first)
