@@ -241,6 +241,9 @@ def main():
     ap.add_argument("--cols", type=int, default=None, help="override the column count (x length) of the workload")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay each step (3 kernels, plus the collective and carry fold at N>1) as one CUDA graph; auto = on")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="mspmv_set_option before the run (opt-in kernel variants, e.g. tile_variant=3, "
+                         "small_fused_tiles=4096); recorded in config.options")
     ap.add_argument("--gather-y", action="store_true",
                     help="N>1: include the all_gather of the y slices in every step (solver-style: the whole y "
                          "on every rank, ready to be the next x)")
@@ -273,6 +276,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.engine:
         ms.lib().mspmv_set_engine(args.engine.encode())
+    options = {}
+    for kv in args.option:
+        k, _, v = kv.partition("=")
+        if ms.lib().mspmv_set_option(k.encode(), int(v)) != 0:
+            raise SystemExit(f"unknown option {kv!r}")
+        options[k] = int(v)
 
     name, kind, dt, p, scaling = workload_spec(args.workload, world)
     if args.cols:
@@ -354,7 +363,8 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(f"{name}@{world}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_tile_kernel" if (args.engine or "tile") != "stream" else "spmv_stream_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": ("spmv_stream_kernel" if (args.engine or "tile") == "stream" else
+                           "spmv_tile3_kernel" if options.get("tile_variant") == 3 else "spmv_tile_kernel"),
                 "algorithmic_bytes_per_launch": shard_bytes,
                 "note": "duration = whole step (search + tile + carry fix-up kernels; the tile kernel is 94.7% of it, profiles/launches_r01.csv), CUDA events"}
 
@@ -435,7 +445,7 @@ def main():
                            kind, "stratified-uniform over all columns, sorted, distinct"),
                        "parallelism": f"merge-path shards x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
-                       "engine": args.engine or "tile", "cuda_graph": use_graph, "gather_y": gather_y},
+                       "engine": args.engine or "tile", "cuda_graph": use_graph, "gather_y": gather_y, "options": options},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "hbm_gbs_algorithmic": achieved * (1 if world == 1 else world),

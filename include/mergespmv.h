@@ -177,7 +177,10 @@ int mspmv_set_engine(const char* name);
  *                        its own merge-path coordinates, the last block to finish folds the
  *                        carries) instead of search + tile + fix-up kernels -- the small-matrix
  *                        overhead the paper names (section IV.B; dispatch_spmv_orig.cuh:674-679).
- *                        0: off (default).  -1: back to the MSPMV_SMALL_FUSED environment value. */
+ *                        0: off (default).  -1: back to the MSPMV_SMALL_FUSED environment value.
+ *   "tile_variant"       2: the shipped tile kernel (default).  3: spmv_tile3_kernel -- thread-blocked
+ *                        gathers, products kept in registers (csrc/spmv_tile3.cuh); same bits.
+ *                        -1: back to the MSPMV_TILE_VARIANT environment value. */
 int mspmv_set_option(const char* name, int value);
 
 #ifdef __cplusplus

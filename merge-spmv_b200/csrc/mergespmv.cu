@@ -19,6 +19,7 @@
 #include "merge_common.cuh"
 #include "spmv_stream.cuh"
 #include "spmv_tile.cuh"
+#include "spmv_tile3.cuh"
 
 namespace mspmv {
 
@@ -88,6 +89,20 @@ static int small_fused_tiles()
         return e ? std::atoi(e) : 0;
     }();
     return env > 0 ? env : 0;
+}
+
+// Tile kernel variant: 2 = tile_body (shipped), 3 = tile_body_v3 (spmv_tile3.cuh; opt-in until timed).
+// MSPMV_TILE_VARIANT=3 or mspmv_set_option("tile_variant", 3).
+static std::atomic<int> g_tile_variant{-1};
+static int tile_variant()
+{
+    int v = g_tile_variant.load(std::memory_order_relaxed);
+    if (v >= 0) return v;
+    static int env = [] {
+        const char* e = std::getenv("MSPMV_TILE_VARIANT");
+        return e ? std::atoi(e) : 2;
+    }();
+    return env == 3 ? 3 : 2;
 }
 
 static inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
@@ -233,10 +248,27 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
             configured[dev & 63] = true;
         }
     }
-    spmv_tile_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
-                                                          carry_vals, alpha, beta, num_rows, num_nonzeros, shift_v,
-                                                          shift_c, shift_r, tile_prefetch_ahead());
-    rc = post_launch("spmv_tile_kernel", grid, block, 0, stream, debug_sync);
+    if (tile_variant() == 3) {
+        static bool v3_configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!v3_configured[dev & 63]) {
+            int pct = 70;
+            if (const char* e = std::getenv("MSPMV_TILE_CARVEOUT")) pct = std::atoi(e);
+            if (pct >= 0)
+                cudaFuncSetAttribute(spmv_tile3_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            v3_configured[dev & 63] = true;
+        }
+        spmv_tile3_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
+                                                               carry_vals, alpha, beta, num_rows, num_nonzeros,
+                                                               shift_v, shift_c, shift_r, tile_prefetch_ahead());
+        rc = post_launch("spmv_tile3_kernel", grid, block, 0, stream, debug_sync);
+    } else {
+        spmv_tile_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
+                                                              carry_vals, alpha, beta, num_rows, num_nonzeros,
+                                                              shift_v, shift_c, shift_r, tile_prefetch_ahead());
+        rc = post_launch("spmv_tile_kernel", grid, block, 0, stream, debug_sync);
+    }
     if (rc) return rc;
     if (p.num_tiles > 1) {  // dispatch_spmv_orig.cuh:721
         dim3 fgrid(p.num_fix_blocks), fblock(C::FIX);
@@ -647,6 +679,11 @@ int mspmv_set_option(const char* name, int value)
     if (!name) return 1;
     if (!std::strcmp(name, "small_fused_tiles")) {
         g_small_fused_tiles = value < 0 ? -1 : value;  // -1: back to the environment / default
+        return 0;
+    }
+    if (!std::strcmp(name, "tile_variant")) {
+        if (value != -1 && value != 2 && value != 3) return 1;
+        g_tile_variant = value;  // -1: back to the environment / default
         return 0;
     }
     return 1;

@@ -332,6 +332,17 @@ inline T atomicExch(T* p, T v)
     return old;
 }
 
+inline float __fmul_rn(float a, float b)
+{
+    volatile float r = a * b;  // volatile: the product is rounded before any use
+    return r;
+}
+inline double __dmul_rn(double a, double b)
+{
+    volatile double r = a * b;
+    return r;
+}
+
 // CUDA's global-namespace integer min / max
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }

@@ -6,6 +6,7 @@
 #include "simt_emu.hpp"
 
 #include "spmv_tile.cuh"
+#include "spmv_tile3.cuh"
 
 #include <vector>
 
@@ -21,7 +22,7 @@ int shift_of(const void* p)
 
 template <typename T, bool AXPBY>
 int run(const T* values, const int* row_offsets, const int* col, const T* x, T* y, int num_rows,
-        int num_nonzeros, T alpha, T beta, int prefetch_ahead, int* stats, bool fused = false)
+        int num_nonzeros, T alpha, T beta, int prefetch_ahead, int* stats, int mode = 0)
 {
     using C = TileCfg<T>;
     if (num_rows <= 0) return 0;
@@ -48,7 +49,7 @@ int run(const T* values, const int* row_offsets, const int* col, const T* x, T* 
         stats[1] = C::TILE;
         stats[2] = C::THREADS;
     }
-    if (fused) {  // single-launch path for small matrices (cudaMemsetAsync of the ticket + one kernel)
+    if (mode == 1) {  // single-launch path for small matrices (cudaMemsetAsync of the ticket + one kernel)
         ticket = 0u;
         emu::launch((unsigned)num_tiles, (unsigned)C::THREADS, [&] {
             spmv_tile_fused_kernel<T, AXPBY>(values, row_offsets, col, x, y, carry_rows, carry_vals, alpha, beta,
@@ -61,9 +62,14 @@ int run(const T* values, const int* row_offsets, const int* col, const T* x, T* 
         tile_search_kernel(row_end, num_rows, num_nonzeros, C::TILE, num_tiles, coords, &ticket);
     });
     emu::launch((unsigned)num_tiles, (unsigned)C::THREADS, [&] {
-        spmv_tile_kernel<T, AXPBY>(values, row_offsets, col, x, y, coords, carry_rows, carry_vals, alpha, beta,
-                                   num_rows, num_nonzeros, shift_of<T>(values), shift_of<int>(col),
-                                   shift_of<int>(row_offsets), prefetch_ahead);
+        if (mode == 3)
+            spmv_tile3_kernel<T, AXPBY>(values, row_offsets, col, x, y, coords, carry_rows, carry_vals, alpha, beta,
+                                        num_rows, num_nonzeros, shift_of<T>(values), shift_of<int>(col),
+                                        shift_of<int>(row_offsets), prefetch_ahead);
+        else
+            spmv_tile_kernel<T, AXPBY>(values, row_offsets, col, x, y, coords, carry_rows, carry_vals, alpha, beta,
+                                       num_rows, num_nonzeros, shift_of<T>(values), shift_of<int>(col),
+                                       shift_of<int>(row_offsets), prefetch_ahead);
     });
     if (num_tiles > 1) {
         emu::launch((unsigned)num_fix_blocks, (unsigned)C::FIX, [&] {
@@ -78,30 +84,18 @@ int run(const T* values, const int* row_offsets, const int* col, const T* x, T* 
 
 extern "C" {
 
+// mode: 0 = search + tile + fix-up (shipped), 1 = single fused launch, 3 = search + tile variant 3 + fix-up
 int emu_csrmv_f64(const double* v, const int* ro, const int* ci, const double* x, double* y, int rows, int nnz,
-                  double alpha, double beta, int axpby, int prefetch_ahead, int* stats)
+                  double alpha, double beta, int axpby, int prefetch_ahead, int* stats, int mode)
 {
-    return axpby ? run<double, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats)
-                 : run<double, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats);
+    return axpby ? run<double, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, mode)
+                 : run<double, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, mode);
 }
 int emu_csrmv_f32(const float* v, const int* ro, const int* ci, const float* x, float* y, int rows, int nnz,
-                  float alpha, float beta, int axpby, int prefetch_ahead, int* stats)
+                  float alpha, float beta, int axpby, int prefetch_ahead, int* stats, int mode)
 {
-    return axpby ? run<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats)
-                 : run<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats);
-}
-
-int emu_csrmv_fused_f64(const double* v, const int* ro, const int* ci, const double* x, double* y, int rows, int nnz,
-                        double alpha, double beta, int axpby, int prefetch_ahead, int* stats)
-{
-    return axpby ? run<double, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, true)
-                 : run<double, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, true);
-}
-int emu_csrmv_fused_f32(const float* v, const int* ro, const int* ci, const float* x, float* y, int rows, int nnz,
-                        float alpha, float beta, int axpby, int prefetch_ahead, int* stats)
-{
-    return axpby ? run<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, true)
-                 : run<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, true);
+    return axpby ? run<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, mode)
+                 : run<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, prefetch_ahead, stats, mode);
 }
 
 // coordinates of arbitrary diagonals through the device search routine (merge_common.cuh)

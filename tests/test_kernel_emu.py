@@ -37,10 +37,11 @@ def build(name):
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, f"libtile_emu_{name}.so")
     srcs = [os.path.join(EMU, f) for f in ("tile_emu.cpp", "simt_emu.hpp", "ptx_emu.cuh")]
-    srcs += [os.path.join(CSRC, f) for f in ("spmv_tile.cuh", "merge_common.cuh", "tma_stage.cuh", "ptx_sm100.cuh")]
+    srcs += [os.path.join(CSRC, f) for f in ("spmv_tile.cuh", "spmv_tile3.cuh", "merge_common.cuh", "tma_stage.cuh",
+                                             "ptx_sm100.cuh")]
     if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(s) for s in srcs + [__file__]):
         return out
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fno-strict-aliasing", "-fno-gnu-unique", "-fPIC", "-shared", "-w",
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fno-strict-aliasing", "-fno-gnu-unique", "-ffp-contract=off", "-fPIC", "-shared", "-w",
            "-I", EMU, "-I", CSRC, "-I", "/usr/local/cuda/include", *VARIANTS[name],
            os.path.join(EMU, "tile_emu.cpp"), "-o", out]
     subprocess.run(cmd, check=True)
@@ -51,14 +52,13 @@ class Emu:
     def __init__(self, name="shipped"):
         self.lib = C.CDLL(build(name))
         for sfx, fp in (("f64", C.c_double), ("f32", C.c_float)):
-            for stem in ("emu_csrmv_", "emu_csrmv_fused_"):
-                f = getattr(self.lib, stem + sfx)
-                f.restype = C.c_int
-                f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p]
+            f = getattr(self.lib, "emu_csrmv_" + sfx)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p, C.c_int]
         self.lib.emu_merge_path_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
 
     def csrmv(self, ro, col, val, x, y_in=None, alpha=1.0, beta=0.0, axpby=False, misalign=(0, 0, 0),
-              prefetch_ahead=0, fused=False):
+              prefetch_ahead=0, fused=False, variant=2):
         """misalign = element offsets (values, col, row_offsets) of the array bases from 16 bytes."""
         dt = val.dtype
         rows, nnz = ro.size - 1, int(ro[-1])
@@ -81,9 +81,10 @@ class Emu:
         xx = np.ascontiguousarray(x, dtype=dt)
         y = np.full(rows, np.nan, dtype=dt) if y_in is None else np.array(y_in, dtype=dt)
         stats = np.zeros(4, np.int32)
-        fn = getattr(self.lib, ("emu_csrmv_fused_" if fused else "emu_csrmv_") + ("f64" if dt == np.float64 else "f32"))
+        fn = getattr(self.lib, "emu_csrmv_" + ("f64" if dt == np.float64 else "f32"))
+        mode = 1 if fused else (3 if variant == 3 else 0)
         rc = fn(v.ctypes.data, r.ctypes.data, c.ctypes.data, xx.ctypes.data, y.ctypes.data, rows, nnz,
-                alpha, beta, int(axpby), prefetch_ahead, stats.ctypes.data)
+                alpha, beta, int(axpby), prefetch_ahead, stats.ctypes.data, mode)
         assert rc == 0
         self.stats = stats
         return y
@@ -244,3 +245,29 @@ def test_emu_fused_single_launch(emu0, orc, dt):
     got = emu0.csrmv(ro, col, val, x, y_in=y0, alpha=-0.75, beta=0.5, axpby=True, fused=True)
     want = (dt(-0.75) * ax + dt(0.5) * y0).astype(dt)
     assert np.all(np.abs(got - want) <= (1e-10 if dt == np.float64 else 3e-6) * (np.abs(0.75 * ax) + np.abs(0.5 * y0)))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_emu_tile_variant3_bit_identical(emu, orc, dt):
+    """tile_body_v3 (thread-blocked gathers, products in registers) performs the same floating-point
+    operations in the same order as tile_body: the results must be bit-identical, for every
+    structure, alignment and for alpha/beta."""
+    rng = np.random.default_rng(33)
+    for rows, cols, mean_len, empty, longs in SHAPES:
+        ro, col = random_csr(rng, rows, cols, mean_len, empty, longs)
+        nnz = int(ro[-1])
+        val = (0.5 + rng.random(nnz)).astype(dt)
+        x = (0.5 + rng.random(cols)).astype(dt)
+        v2 = emu.csrmv(ro, col, val, x)
+        v3 = emu.csrmv(ro, col, val, x, variant=3)
+        assert np.array_equal(v2, v3), (rows, cols)
+        assert_close(v3, orc.merge_csrmv(ro, col, val, x, num_threads=8), ro, dt, f"{rows}x{cols}")
+    ro, col = random_csr(rng, 700, 900, 7, 0.2, 1)
+    nnz = int(ro[-1])
+    val = (0.5 + rng.random(nnz)).astype(dt)
+    x = (0.5 + rng.random(900)).astype(dt)
+    y0 = rng.random(700).astype(dt)
+    for mis in ((0, 0, 0), (1, 2, 3), (1, 1, 0), (0, 3, 1)):
+        a = emu.csrmv(ro, col, val, x, y_in=y0, alpha=1.5, beta=-0.5, axpby=True, misalign=mis)
+        b = emu.csrmv(ro, col, val, x, y_in=y0, alpha=1.5, beta=-0.5, axpby=True, misalign=mis, variant=3)
+        assert np.array_equal(a, b), mis

@@ -6,7 +6,10 @@ They are off by default in the library, so these tests are off by default too:
 
 The file sorts last so that `pytest -x` reaches it only after the shipped path has passed.
 Current subjects:
-  * small_fused_tiles  -- the single-launch path for small matrices (spmv_tile_fused_kernel).
+  * small_fused_tiles  -- the single-launch path for small matrices (spmv_tile_fused_kernel);
+  * tile_variant=3     -- thread-blocked gathers with the products in registers (spmv_tile3_kernel):
+                          same floating-point operations in the same order, so bit-identical to the
+                          shipped kernel.
 """
 import os
 
@@ -17,6 +20,7 @@ import torch
 from conftest import random_csr
 
 import merge_spmv_b200 as ms
+from merge_spmv_b200 import generators as gen
 from merge_spmv_b200.csrmv import csrmv_config
 
 pytestmark = [pytest.mark.gpu,
@@ -92,3 +96,47 @@ def test_fused_in_cuda_graph(fused):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(y, first)
+
+
+@pytest.fixture
+def variant3():
+    yield lambda on: ms.lib().mspmv_set_option(b"tile_variant", 3 if on else 2)
+    assert ms.lib().mspmv_set_option(b"tile_variant", -1) == 0
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_variant3_bit_identical_random_structures(orc, variant3, dt):
+    rng = np.random.default_rng(404)
+    shapes = [(1, 1, 1.0, 0.0, 0), (1, 50, 20, 0.0, 0), (17, 1, 1.0, 0.3, 0), (100, 64, 0.0, 1.0, 0),
+              (5000, 300, 0.05, 0.9, 0), (3000, 4000, 9, 0.1, 2), (257, 100000, 700, 0.0, 3),
+              (20000, 20000, 3, 0.3, 1), (1, 200000, 150000, 0.0, 1), (70000, 128, 2, 0.5, 0),
+              (4099, 4099, 31, 0.01, 0)]
+    for rows, cols, mean_len, empty, longs in shapes:
+        ro, col = random_csr(rng, rows, cols, mean_len, empty, longs)
+        nnz = int(ro[-1])
+        val = (0.5 + rng.random(nnz)).astype(dt)
+        x = (0.5 + rng.random(cols)).astype(dt)
+        variant3(False)
+        v2 = gpu_csrmv(ro, col, val, x)
+        variant3(True)
+        v3 = gpu_csrmv(ro, col, val, x)
+        assert np.array_equal(v2, v3), (rows, cols)
+        want = orc.merge_csrmv(ro, col, val, x, num_threads=8)
+        err = np.abs(v3.astype(np.float64) - want.astype(np.float64))
+        assert np.all(err <= tol_for(ro, dt) * np.maximum(np.abs(want), 1e-300)), (rows, cols)
+        y = gpu_csrmv(ro, col, np.ones(nnz, dt), np.ones(cols, dt))
+        assert np.array_equal(y, np.diff(ro).astype(dt)), (rows, cols, "exact")
+
+
+@pytest.mark.parametrize("name", ["uniform_1m_64", "powerlaw_2m", "banded_10m"])
+def test_variant3_bit_identical_full_size(variant3, name):
+    """BASELINE.json configs 2-4 at full size: variant 3 against the shipped kernel, bit for bit."""
+    kind, dt, p = gen.CONFIGS[name]
+    m = gen.make_config(name, values="random", dtype=dt, device=DEV)
+    x = gen.vector(m.cols, dt, "random", device=DEV)
+    variant3(False)
+    y2 = ms.csrmv(m.row_offsets, m.col, m.val, x).clone()
+    variant3(True)
+    y3 = ms.csrmv(m.row_offsets, m.col, m.val, x)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y3)

@@ -1,0 +1,63 @@
+#!/usr/bin/env bash
+# First GPU call of the next round: parity of the opt-in variants, then one timing table of every
+# variant on the four single-GPU workloads.  Everything lands in gpurun_out/ (merged back by gpurun).
+#
+#   gpurun --timeout 1500 -- 'bash tools/round2_sweep.sh'
+#
+# Variants (all off by default; kernel logic already covered on CPU by tests/test_kernel_emu.py):
+#   tile_variant=3          thread-blocked gathers, products in registers (csrc/spmv_tile3.cuh)
+#   small_fused_tiles=N     single launch for matrices of <= N tiles (config 1 and other small inputs)
+#   MSPMV_TILE_PREFETCH=N   L2 prefetch N tiles ahead (measured r01: +2 % banded, -4 % random)
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out
+mkdir -p "$OUT"
+PY=python
+STEPS=${STEPS:-300}
+
+echo "== parity of the opt-in variants" | tee "$OUT/sweep_r02.txt"
+MSPMV_TEST_EXPERIMENTAL=1 timeout 900 $PY -m pytest tests/test_zz_experimental.py -m gpu -q -x 2>&1 | tail -5 | tee -a "$OUT/sweep_r02.txt"
+
+run() {  # label, env assignments..., -- bench args
+    local label=$1; shift
+    local envs=()
+    while [ "$1" != "--" ]; do envs+=("$1"); shift; done
+    shift
+    local line
+    line=$(env "${envs[@]}" timeout 600 $PY bench.py --no-cpu-baseline --no-e2e --steps "$STEPS" --warmup 10 "$@" 2>/dev/null | tail -1)
+    $PY - "$label" "$line" <<'PYEOF' | tee -a "$OUT/sweep_r02.txt"
+import json, sys
+label, line = sys.argv[1], sys.argv[2]
+try:
+    d = json.loads(line)
+    r = d["roofline"]
+    sec = r.get("secondary") or {}
+    print(f"{label:34s} {d['config']['workload']:22s} {d['ms_per_step']:.4f} ms  {d['value']:8.1f} GFLOP/s  "
+          f"hbm frac {r['frac']:.3f}  gather frac {sec.get('frac', float('nan')):.3f}  "
+          f"clk {d['clocks'].get('sm_mhz')} {d['clocks'].get('reasons')}")
+except Exception as e:
+    print(f"{label:34s} FAILED: {e}: {line[:200]}")
+PYEOF
+}
+
+echo "== timing: ms per CsrMV step (CUDA-graph replay, $STEPS steps)" | tee -a "$OUT/sweep_r02.txt"
+for W in uniform_1m_64 powerlaw_2m banded_10m uniform_1m_64_local; do
+    run "shipped"                 -- --workload $W
+    run "tile_variant=3"          -- --workload $W --option tile_variant=3
+    run "tile_variant=3 carve 56" MSPMV_TILE_CARVEOUT=56 -- --workload $W --option tile_variant=3
+done
+echo "== small matrices (config 1 shape): launch-latency-bound" | tee -a "$OUT/sweep_r02.txt"
+run "shipped (3 launches)"        -- --workload cpu_uniform_16k --steps 2000
+run "small_fused_tiles=4096"      -- --workload cpu_uniform_16k --steps 2000 --option small_fused_tiles=4096
+run "shipped, eager launches"     -- --workload cpu_uniform_16k --steps 2000 --graph off
+run "fused, eager launches"       -- --workload cpu_uniform_16k --steps 2000 --graph off --option small_fused_tiles=4096
+
+# one ncu capture of the candidate kernel next to the shipped one (banded: the issue-bound case)
+if command -v ncu >/dev/null; then
+    for V in 2 3; do
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmv_tile -c 1 \
+            -o "$OUT/ncu_r02_banded_v$V" -f $PY bench.py --workload banded_10m --steps 2 --warmup 3 \
+            --no-cpu-baseline --no-e2e --graph off --option tile_variant=$V > "$OUT/ncu_r02_banded_v$V.log" 2>&1
+    done
+fi
+echo "done" | tee -a "$OUT/sweep_r02.txt"
