@@ -14,6 +14,13 @@
 
 #include "spmv_tile.cuh"
 
+#ifndef MSPMV_V3_MIN_BLOCKS
+#define MSPMV_V3_MIN_BLOCKS 12  // register budget: 65536 / (128 * 12) = 42 -> 40 registers per thread, like tile_body
+#endif
+#ifndef MSPMV_V3_XS_SCATTER
+#define MSPMV_V3_XS_SCATTER 1  // 1: start rows scattered by the row owners; 0: popcount prefix as in tile_body
+#endif
+
 namespace mspmv {
 
 template <typename T, bool AXPBY>
@@ -34,6 +41,9 @@ __device__ __forceinline__ void tile_body_v3(
     alignas(16) __shared__ uint32_t s_bits[C::BW];
     alignas(16) __shared__ Seg<T> s_warp[NW];
     alignas(8) __shared__ uint64_t s_bar;
+#if MSPMV_V3_XS_SCATTER
+    alignas(16) __shared__ int s_xs[C::THREADS];  // start row of every thread, written by the row owners
+#endif
 
     const int warp = tid >> 5, lane = tid & 31;
     const int x0 = c0.x, y0 = c0.y;
@@ -53,6 +63,9 @@ __device__ __forceinline__ void tile_body_v3(
         fence_mbar_init();
     }
     if (tid < C::BW) s_bits[tid] = 0u;
+#if MSPMV_V3_XS_SCATTER
+    s_xs[tid] = nrows;  // threads that start after the tile's last row end
+#endif
     __syncthreads();
 
     // ---- TMA staging of the tile (warp 0) -----------------------------------------------------
@@ -84,6 +97,33 @@ __device__ __forceinline__ void tile_body_v3(
     mbar_wait(&s_bar, 0);
 
     // ---- row-end flags: merge item p = row_end[r] - y0 + r is the end of local row r ------------
+#if MSPMV_V3_XS_SCATTER
+    // The thread that owns row r also tells every thread t whose first merge item lies in
+    // (end of row r-1, end of row r] that it starts at row r: xs(t) = #{rows ending before t*IPT} --
+    // the coordinate the reference finds with a per-thread MergePathSearch
+    // (agent_spmv_orig.cuh:539-545) -- without any per-thread popcount prefix.  A range covers
+    // ceil(row length / IPT) threads, so the loop is short except for rows that span most of a tile.
+    for (int r = tid; r < nrows; r += C::THREADS) {
+        int e, ep;
+        if (nrows <= C::ROWCAP) {
+            e = s_row[off_r + r];
+            ep = r > 0 ? s_row[off_r + r - 1] : y0 - r;  // r == 0: previous end position -1
+        } else {
+            e = __ldg(row_offsets + jr0 + r);
+            ep = r > 0 ? __ldg(row_offsets + jr0 + r - 1) : y0 - r;
+        }
+        const int pos = e - y0 + r;
+        const int prev = ep - y0 + r - 1;
+        atomicOr(&s_bits[pos >> 5], 1u << (pos & 31));
+        const int t_hi = pos / IPT;
+        for (int t = (prev + IPT) / IPT; t <= t_hi; ++t) s_xs[t] = r;
+    }
+    __syncthreads();
+    const int diag = tid * IPT;
+    const uint32_t w0 = s_bits[diag >> 5], w1 = s_bits[(diag >> 5) + 1];
+    const uint32_t bits = __funnelshift_r(w0, w1, diag & 31) & ((1u << IPT) - 1u);
+    const int xs = s_xs[tid];
+#else
     for (int r = tid; r < nrows; r += C::THREADS) {
         const int e = nrows <= C::ROWCAP ? s_row[off_r + r] : __ldg(row_offsets + jr0 + r);
         const int pos = e - y0 + r;
@@ -106,6 +146,8 @@ __device__ __forceinline__ void tile_body_v3(
     for (int k = 0; k < IPT - 1; ++k)
         if (warp * IPT + k < (diag >> 5)) in_warp += __popc(s_bits[warp * IPT + k]);
     const int xs = before_warp + in_warp;
+
+#endif
 
     // ---- thread-blocked loads: my nonzeros are the contiguous run k0 .. of the tile's nonzeros ----
     // `skip` bit i: merge item i of mine is not a nonzero (a row end, or past the end of the last
@@ -185,7 +227,7 @@ __device__ __forceinline__ void tile_body_v3(
 }
 
 template <typename T, bool AXPBY>
-__global__ __launch_bounds__(TileCfg<T>::THREADS) void spmv_tile3_kernel(
+__global__ __launch_bounds__(TileCfg<T>::THREADS, MSPMV_V3_MIN_BLOCKS) void spmv_tile3_kernel(
     const T* __restrict__ values, const int* __restrict__ row_offsets,
     const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
     const int2* __restrict__ coords, int* __restrict__ carry_rows, T* __restrict__ carry_vals, T alpha,

@@ -40,11 +40,15 @@ except Exception as e:
 PYEOF
 }
 
+make -C merge-spmv_b200 -s -j4 variants 2>&1 | tail -3
+V=merge-spmv_b200/variants
 echo "== timing: ms per CsrMV step (CUDA-graph replay, $STEPS steps)" | tee -a "$OUT/sweep_r02.txt"
 for W in uniform_1m_64 powerlaw_2m banded_10m uniform_1m_64_local; do
     run "shipped"                 -- --workload $W
     run "tile_variant=3"          -- --workload $W --option tile_variant=3
     run "tile_variant=3 carve 56" MSPMV_TILE_CARVEOUT=56 -- --workload $W --option tile_variant=3
+    run "tile_variant=3, popcount prefix" MSPMV_LIB=$V/libmergespmv_v3popc.so -- --workload $W --option tile_variant=3
+    run "tile_variant=3, 48 registers"  MSPMV_LIB=$V/libmergespmv_v3regs48.so -- --workload $W --option tile_variant=3
 done
 echo "== small matrices (config 1 shape): launch-latency-bound" | tee -a "$OUT/sweep_r02.txt"
 run "shipped (3 launches)"        -- --workload cpu_uniform_16k --steps 2000
