@@ -244,6 +244,9 @@ def main():
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="mspmv_set_option before the run (opt-in kernel variants, e.g. tile_variant=3, "
                          "small_fused_tiles=4096); recorded in config.options")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="N>1: how the carries travel -- nccl: one all_gather + fold kernel (default); p2p: one kernel "
+                         "per rank storing into the peers' symmetric memory over NVLink (csrc/carry_exchange.cuh)")
     ap.add_argument("--gather-y", action="store_true",
                     help="N>1: include the all_gather of the y slices in every step (solver-style: the whole y "
                          "on every rank, ready to be the next x)")
@@ -295,7 +298,7 @@ def main():
 
     shard = sharded.make_shard(ro_np, cols, rank, world,
                                lambda k0, k1: fill(kind, ro, cols, k0, k1, dt, args.values, dev, p), dev)
-    op = sharded.ShardedSpmv(shard)
+    op = sharded.ShardedSpmv(shard, exchange=args.exchange if world > 1 else "nccl")
     L = ms.lib()
 
     def barrier():
@@ -445,7 +448,8 @@ def main():
                            kind, "stratified-uniform over all columns, sorted, distinct"),
                        "parallelism": f"merge-path shards x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
-                       "engine": args.engine or "tile", "cuda_graph": use_graph, "gather_y": gather_y, "options": options},
+                       "engine": args.engine or "tile", "cuda_graph": use_graph, "gather_y": gather_y, "options": options,
+                       "carry_exchange": (args.exchange if world > 1 else None)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "hbm_gbs_algorithmic": achieved * (1 if world == 1 else world),

@@ -130,6 +130,23 @@ int mspmv_apply_carries_f64(double* d_y_local, int y_row_begin, int y_rows, int 
                             const int* d_carry_rows, const double* d_carry_vals, int num_shards,
                             mspmv_stream_t stream);
 
+/* The same exchange step over NVLink peer memory, fused with the fold, in ONE launch per rank and
+ * without NCCL (csrc/carry_exchange.cuh): every rank stores its carry -- the last of the
+ * local_rows entries of d_y_local -- directly into each peer's exchange buffer and releases a flag;
+ * it then waits for the p flags in its own buffer and folds carries 0..p-2 exactly like
+ * mspmv_apply_carries_*.  d_peer_bufs is a DEVICE array of num_shards pointers, entry g = rank g's
+ * exchange buffer as mapped into this process (symmetric memory: cudaIpc / VMM peer mapping, e.g.
+ * torch.distributed._symmetric_memory), each mspmv_exchange_buffer_bytes(num_shards) bytes and
+ * zero-filled before the first call; d_epoch is a zero-initialised device counter private to the
+ * rank.  Every rank must make the same sequence of calls; safe to capture into a CUDA graph. */
+size_t mspmv_exchange_buffer_bytes(int num_shards);
+int mspmv_exchange_carries_f32(float* d_y_local, int local_rows, int y_row_begin, int y_rows,
+                               int num_rows_global, const int* d_carry_rows, void* const* d_peer_bufs,
+                               int rank, int num_shards, unsigned long long* d_epoch, mspmv_stream_t stream);
+int mspmv_exchange_carries_f64(double* d_y_local, int local_rows, int y_row_begin, int y_rows,
+                               int num_rows_global, const int* d_carry_rows, void* const* d_peer_bufs,
+                               int rank, int num_shards, unsigned long long* d_epoch, mspmv_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------
  * 4. Host-buffer operator ("session"): the gpu_spmv driver's own protocol -- upload the CSR
  *    once (gpu_spmv.cu:542-556), then apply it repeatedly (:421-432) -- behind one handle, so

@@ -21,6 +21,9 @@ SIGNATURES = {
     "mspmv_shard_row_offsets": (None, [_vp, _i, _i, _i, _i, _vp]),
     "mspmv_apply_carries_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "mspmv_apply_carries_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "mspmv_exchange_buffer_bytes": (_sz, [_i]),
+    "mspmv_exchange_carries_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "mspmv_exchange_carries_f64": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "mspmv_session_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mspmv_session_apply": (_i, [_vp, _vp, _vp]),
     "mspmv_session_apply_many": (_i, [_vp, _i, _vp, _vp]),

@@ -20,6 +20,7 @@
 #include "spmv_stream.cuh"
 #include "spmv_tile.cuh"
 #include "spmv_tile3.cuh"
+#include "carry_exchange.cuh"
 
 namespace mspmv {
 
@@ -328,6 +329,20 @@ static int apply_carries(T* y_local, int y_row_begin, int y_rows, int num_rows_g
     return post_launch("apply_carries_kernel", dim3(1), dim3(32), 0, stream, 0);
 }
 
+template <typename T>
+static int exchange_carries(T* y_local, int local_rows, int y_row_begin, int y_rows, int num_rows_global,
+                            const int* carry_rows, void* const* peer_bufs, int rank, int num_shards,
+                            unsigned long long* epoch, void* stream_v)
+{
+    if (!y_local || !carry_rows || !peer_bufs || !epoch || local_rows < 1 || rank < 0 || rank >= num_shards)
+        return (int)cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    carry_exchange_kernel<T><<<1, 32, 0, stream>>>(y_local, local_rows - 1, y_row_begin, y_rows, num_rows_global,
+                                                   carry_rows, reinterpret_cast<uint64_t* const*>(peer_bufs), rank,
+                                                   num_shards, epoch, kExchangePhasePush | kExchangePhaseFold);
+    return post_launch("carry_exchange_kernel", dim3(1), dim3(32), 0, stream, 0);
+}
+
 static void host_search(const int* row_offsets, int num_rows, int num_nonzeros, int64_t diagonal,
                         int* out_x, int* out_y)
 {
@@ -479,6 +494,20 @@ int mspmv_apply_carries_f64(double* y, int b, int n, int rows_global, const int*
                             int shards, mspmv_stream_t s)
 {
     return apply_carries<double>(y, b, n, rows_global, cr, cv, shards, s);
+}
+
+size_t mspmv_exchange_buffer_bytes(int num_shards) { return sizeof(uint64_t) * 4u * (size_t)(num_shards > 0 ? num_shards : 0); }
+int mspmv_exchange_carries_f32(float* y, int local_rows, int b, int n, int rows_global, const int* cr,
+                               void* const* peer_bufs, int rank, int shards, unsigned long long* epoch,
+                               mspmv_stream_t s)
+{
+    return exchange_carries<float>(y, local_rows, b, n, rows_global, cr, peer_bufs, rank, shards, epoch, s);
+}
+int mspmv_exchange_carries_f64(double* y, int local_rows, int b, int n, int rows_global, const int* cr,
+                               void* const* peer_bufs, int rank, int shards, unsigned long long* epoch,
+                               mspmv_stream_t s)
+{
+    return exchange_carries<double>(y, local_rows, b, n, rows_global, cr, peer_bufs, rank, shards, epoch, s);
 }
 
 // ---- session -----------------------------------------------------------------------------------

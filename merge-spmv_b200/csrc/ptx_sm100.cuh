@@ -102,6 +102,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// System-scope accesses for data exchanged with peer GPUs over NVLink (carry exchange): a relaxed
+// 64-bit store into peer memory, and an acquire load to poll a flag a peer writes into local memory.
+__device__ __forceinline__ void st_relaxed_sys_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // L2 prefetch of `bytes` (multiple of 16) at a 16-byte-aligned global address (SASS UBLKPF.L2)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
 {

@@ -121,9 +121,16 @@ def apply_carries(y_local, shard: Shard, carry_vals, stream=None):
 class ShardedSpmv:
     """y_shard = (A x)[x_g : x_{g+1}) on this rank; call collectively on all ranks."""
 
-    def __init__(self, shard: Shard, group=None, local_spmv=None, fold=None):
+    def __init__(self, shard: Shard, group=None, local_spmv=None, fold=None, exchange="nccl"):
+        """``exchange``: how the p carry values travel.  "nccl" (default): one ``all_gather`` + the fold
+        kernel.  "p2p": ONE kernel per rank that stores its carry straight into every peer's
+        symmetric-memory buffer over NVLink, waits for the peers' flags and folds
+        (``mspmv_exchange_carries_*``, csrc/carry_exchange.cuh) -- no NCCL on the data path."""
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
         self.shard = shard
         self.group = group
+        self._exchange = exchange
         dev = shard.val.device
         # y slices have different lengths (equal WORK per rank, not equal rows): the exchange of y
         # (gather_y) sends fixed-size records of `pad` rows, so the local result lives at the head
@@ -138,6 +145,41 @@ class ShardedSpmv:
         self._local_spmv = local_spmv or (lambda s, x, y: csrmv(s.row_offsets, s.col, s.val, x, y,
                                                                num_cols=s.cols))
         self._fold = fold or apply_carries
+        if exchange == "p2p" and shard.world > 1:
+            self._setup_p2p()
+
+    def _setup_p2p(self):
+        """Symmetric exchange buffers: 4*p 64-bit words per rank (values[2][p], flags[2][p]), mapped
+        into every process of the group (torch.distributed._symmetric_memory: cudaIpc / VMM)."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        s = self.shard
+        dev = self.y_local.device
+        if dev.type != "cuda":
+            raise _lib.MergeSpmvError("the p2p carry exchange needs CUDA devices with peer access (NVLink)")
+        group = self.group if self.group is not None else dist.group.WORLD
+        nbytes = _lib.lib().mspmv_exchange_buffer_bytes(s.world)
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass  # newer torch enables it on rendezvous
+        self._xbuf = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=dev)
+        self._xbuf.zero_()
+        self._xhdl = symm_mem.rendezvous(self._xbuf, group.group_name)
+        if self._xhdl.world_size != s.world or self._xhdl.rank != s.rank:
+            raise _lib.MergeSpmvError("symmetric-memory group does not match the shard layout")
+        torch.cuda.synchronize(dev)
+        self._xhdl.barrier()  # every buffer is zero before anybody pushes
+        self._epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def _exchange_p2p(self):
+        s = self.shard
+        sfx = "f64" if self.y_local.dtype == torch.float64 else "f32"
+        fn = getattr(_lib.lib(), f"mspmv_exchange_carries_{sfx}")
+        with torch.cuda.device(self.y_local.device):
+            _lib.check(fn(_ptr(self.y_local), s.local_rows, s.x0, s.owned_rows, s.rows_global,
+                          _ptr(s.carry_rows), C.c_void_p(int(self._xhdl.buffer_ptrs_dev)), s.rank, s.world,
+                          _ptr(self._epoch), _stream(None)), "exchange_carries")
 
     def capture(self, x, gather_y=False):
         """Record one whole step (search + tile + fix-up kernels, the all_gather, the carry fold --
@@ -193,7 +235,9 @@ class ShardedSpmv:
     def __call__(self, x):
         s = self.shard
         self._local_spmv(s, x, self.y_local)
-        if s.world > 1:
+        if s.world > 1 and self._exchange == "p2p":
+            self._exchange_p2p()  # push over NVLink + wait + fold, one launch
+        elif s.world > 1:
             # the single exchange step: p carry values, taken in place from the last local row
             dist.all_gather_into_tensor(self.carries, self.y_local[s.local_rows - 1:], group=self.group)
             self._fold(self.y_local, s, self.carries)

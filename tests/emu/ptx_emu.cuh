@@ -99,6 +99,24 @@ inline void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
     if (((uintptr_t)src_gmem & 15) || (bytes & 15) || bytes == 0)
         emu::die("cp.async.bulk.prefetch: address must be 16-byte aligned and the size a non-zero multiple of 16");
 }
+inline void st_relaxed_sys_u64(uint64_t* p, uint64_t v) { *p = v; }
+inline void st_release_sys_u64(uint64_t* p, uint64_t v) { *p = v; }
+inline uint64_t ld_acquire_sys_u64(const uint64_t* p)
+{
+    // a thread that reads the same address and gets the same value again is spinning: give the other
+    // threads a turn without counting it as progress (so a flag nobody sets ends as a reported deadlock)
+    static const uint64_t* last_addr[emu::kMaxThreads];
+    static uint64_t last_val[emu::kMaxThreads];
+    const int t = emu::S().cur;
+    const uint64_t v = *reinterpret_cast<const volatile uint64_t*>(p);
+    if (last_addr[t] == p && last_val[t] == v) {
+        emu::yield();
+        return *reinterpret_cast<const volatile uint64_t*>(p);
+    }
+    last_addr[t] = p;
+    last_val[t] = v;
+    return v;
+}
 inline void fence_proxy_async() {}
 inline void named_bar_sync(int id, int threads) { emu::block_barrier(id, threads); }
 

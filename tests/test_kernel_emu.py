@@ -39,7 +39,7 @@ def build(name):
     out = os.path.join(out_dir, f"libtile_emu_{name}.so")
     srcs = [os.path.join(EMU, f) for f in ("tile_emu.cpp", "simt_emu.hpp", "ptx_emu.cuh")]
     srcs += [os.path.join(CSRC, f) for f in ("spmv_tile.cuh", "spmv_tile3.cuh", "merge_common.cuh", "tma_stage.cuh",
-                                             "ptx_sm100.cuh")]
+                                             "ptx_sm100.cuh", "carry_exchange.cuh")]
     if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(s) for s in srcs + [__file__]):
         return out
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fno-strict-aliasing", "-fno-gnu-unique", "-ffp-contract=off", "-fPIC", "-shared", "-w",
@@ -272,3 +272,36 @@ def test_emu_tile_variant3_bit_identical(emu, orc, dt):
         a = emu.csrmv(ro, col, val, x, y_in=y0, alpha=1.5, beta=-0.5, axpby=True, misalign=mis)
         b = emu.csrmv(ro, col, val, x, y_in=y0, alpha=1.5, beta=-0.5, axpby=True, misalign=mis, variant=3)
         assert np.array_equal(a, b), mis
+
+
+@pytest.mark.parametrize("use_f32", [0, 1])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_emu_nvlink_carry_exchange(emu0, world, use_f32):
+    """carry_exchange_kernel (peer-memory push + flag, then wait + fold) with `world` simulated
+    ranks over several steps: slot indexing, the epoch-parity double buffer, the fold order of
+    cpu_spmv.cpp:348-352 (a row spanning several ranks takes every carry; carries of rows >= rows
+    are dropped; the last rank's carry is never applied)."""
+    rng = np.random.default_rng(world)
+    steps = 5
+    rows = 40
+    cuts = np.zeros(world + 1, np.int32)
+    cuts[1:-1] = np.sort(rng.integers(0, rows + 1, world - 1))
+    cuts[-1] = rows
+    if world == 8:
+        cuts[3] = cuts[4] = cuts[5]  # ranks 3 and 4 own no row: one long row spans them
+    carry_rows = np.ascontiguousarray(cuts[1:]).astype(np.int32)  # rank g's carry belongs to global row cuts[g+1]
+    carries = rng.integers(1, 50, (steps, world)).astype(np.float64)
+    y = np.zeros((steps, rows), np.float64)
+    lib = emu0.lib
+    lib.emu_exchange_f64.restype = C.c_int
+    lib.emu_exchange_f64.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = lib.emu_exchange_f64(world, steps, cuts.ctypes.data, carry_rows.ctypes.data, carries.ctypes.data,
+                              y.ctypes.data, use_f32)
+    assert rc == 0, "every rank must have advanced its epoch counter once per step"
+    for st in range(steps):
+        want = 100.0 * st + np.arange(rows, dtype=np.float64)
+        for g in range(world - 1):
+            r = int(carry_rows[g])
+            if r < rows:
+                want[r] += carries[st, g]
+        assert np.array_equal(y[st], want), (st, cuts.tolist())

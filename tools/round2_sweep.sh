@@ -56,6 +56,22 @@ run "small_fused_tiles=4096"      -- --workload cpu_uniform_16k --steps 2000 --o
 run "shipped, eager launches"     -- --workload cpu_uniform_16k --steps 2000 --graph off
 run "fused, eager launches"       -- --workload cpu_uniform_16k --steps 2000 --graph off --option small_fused_tiles=4096
 
+# multi-GPU (run this script under `gpurun --gpus 2`): NCCL all_gather + fold vs the NVLink peer-memory
+# exchange kernel, and the solver-style step with the y all_gather
+NGPU=$(nvidia-smi -L 2>/dev/null | wc -l)
+if [ "$NGPU" -ge 2 ]; then
+    echo "== $NGPU GPUs: carry exchange" | tee -a "$OUT/sweep_r02.txt"
+    MSPMV_TEST_EXPERIMENTAL=1 timeout 900 $PY -m pytest tests/test_multi_gpu.py -m gpu -q -x 2>&1 | tail -3 | tee -a "$OUT/sweep_r02.txt"
+    for X in nccl p2p; do
+        line=$(timeout 900 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node "$NGPU" --master-addr 127.0.0.1 \
+               --master-port 29517 bench.py --gpus "$NGPU" --steps "$STEPS" --warmup 10 --no-e2e --exchange $X 2>/dev/null | tail -1)
+        echo "exchange=$X: $line" | cut -c1-400 | tee -a "$OUT/sweep_r02.txt"
+    done
+    line=$(timeout 900 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node "$NGPU" --master-addr 127.0.0.1 \
+           --master-port 29518 bench.py --gpus "$NGPU" --steps "$STEPS" --warmup 10 --no-e2e --gather-y 2>/dev/null | tail -1)
+    echo "gather-y: $line" | cut -c1-400 | tee -a "$OUT/sweep_r02.txt"
+fi
+
 # one ncu capture of the candidate kernel next to the shipped one (banded: the issue-bound case)
 if command -v ncu >/dev/null; then
     for V in 2 3; do
