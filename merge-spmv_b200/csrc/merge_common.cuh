@@ -127,19 +127,41 @@ __device__ __forceinline__ Seg<T> warp_seg_scan_inclusive(Seg<T> s, int lane)
     return s;
 }
 
+// Same result, fewer instructions: one ballot tells every lane where its segment starts (the last
+// lane below it that closed a row), so the shuffle rounds carry only the value and the flag of the
+// result is a mask test.  After round d a lane holds the sum of lanes [max(start, lane-2d+1), lane];
+// a lane adds lane-d's partial only if that lane is inside its segment, and a lane that closed a
+// row itself never adds -- exactly seg_combine applied left to right.
+template <typename T>
+__device__ __forceinline__ Seg<T> warp_seg_scan_inclusive_ballot(Seg<T> s, int lane)
+{
+    const unsigned m = __ballot_sync(kFull, s.ended != 0);
+    if (m == kFull) return s;
+    const unsigned below = m & ((1u << lane) - 1u);
+    // first lane whose partial I may add; 32 (nobody) if I closed a row myself
+    const int start = s.ended ? 32 : (below ? 31 - __clz((int)below) : 0);
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+        T v = shfl_up(s.val, d);
+        if (lane - d >= start) s.val += v;
+    }
+    s.ended = (m & ((2u << lane) - 1u)) != 0u;
+    return s;
+}
+
 // Block-wide exclusive segmented scan over NWARPS*32 threads (all must call).
 //   in        this thread's element
 //   carry_in  element logically preceding thread 0 (the previous tile's carry-out, or {0,0})
 //   excl      out: combine(carry_in, elements of threads 0..t-1)
 //   total     out: combine(carry_in, all elements) -- identical in every thread
 // s_warp must hold NWARPS Seg<T>.  Contains one named barrier among the participating threads.
-template <typename T, int NWARPS>
+template <typename T, int NWARPS, bool BALLOT = false>
 __device__ __forceinline__ void block_seg_scan_exclusive(Seg<T> in, Seg<T> carry_in, Seg<T>* s_warp,
                                                          int tid, int barrier_id, Seg<T>& excl,
                                                          Seg<T>& total)
 {
     const int lane = tid & 31, warp = tid >> 5;
-    Seg<T> inc = warp_seg_scan_inclusive(in, lane);
+    Seg<T> inc = BALLOT ? warp_seg_scan_inclusive_ballot(in, lane) : warp_seg_scan_inclusive(in, lane);
     if (lane == 31) s_warp[warp] = inc;
 
     Seg<T> prev;  // warp-exclusive

@@ -17,6 +17,9 @@
 #ifndef MSPMV_V3_MIN_BLOCKS
 #define MSPMV_V3_MIN_BLOCKS 12  // register budget: 65536 / (128 * 12) = 42 -> 40 registers per thread, like tile_body
 #endif
+#ifndef MSPMV_V3_BALLOT_SCAN
+#define MSPMV_V3_BALLOT_SCAN 1  // 1: ballot-driven warp segmented scan (value-only shuffles); 0: the scan of tile_body
+#endif
 #ifndef MSPMV_V3_XS_SCATTER
 #define MSPMV_V3_XS_SCATTER 1  // 1: start rows scattered by the row owners; 0: popcount prefix as in tile_body
 #endif
@@ -203,7 +206,7 @@ __device__ __forceinline__ void tile_body_v3(
     elem.ended = bits != 0u;
     zero.val = T(0);
     zero.ended = 0;
-    block_seg_scan_exclusive<T, NW>(elem, zero, s_warp, tid, 1, excl, total);
+    block_seg_scan_exclusive<T, NW, MSPMV_V3_BALLOT_SCAN != 0>(elem, zero, s_warp, tid, 1, excl, total);
 
     // ---- finished rows to y from registers; my first row end also takes the carry-in -------------
     {
