@@ -90,3 +90,24 @@ def test_shard_row_offsets_cover_matrix():
             assert lro.size == x1 - x0 + 2
             total += lro[-1]
         assert total == ro[-1]
+
+
+def test_default_kernels_are_the_measured_ones():
+    """The numbers in profiles/ and DESIGN.md section 5 were measured with a specific build.  Every
+    kernel of that build must still be in libmergespmv.so with the same SASS (operand order inside
+    an instruction aside), so that work done without GPU time cannot silently change what the
+    bench runs by default.  After a kernel is changed on purpose AND re-measured, regenerate the
+    file: python tools/sass_fingerprint.py > profiles/sass_fingerprint_rNN.json."""
+    import importlib.util
+    import json
+    import shutil
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    spec = importlib.util.spec_from_file_location("sass_fingerprint", os.path.join(ROOT, "tools", "sass_fingerprint.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    measured = json.load(open(os.path.join(ROOT, "profiles", "sass_fingerprint_r01.json")))
+    now = mod.fingerprint(os.path.join(ROOT, "merge-spmv_b200", "libmergespmv.so"))
+    changed = [k for k, v in measured.items() if now.get(k) != v]
+    assert not changed, f"kernels differ from the measured build: {changed}"
