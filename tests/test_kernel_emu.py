@@ -71,7 +71,7 @@ class Emu:
             base = (-(buf.ctypes.data // a.itemsize)) % per16  # first 16-byte aligned element
             view = buf[base + k: base + k + a.size]
             view[:] = a
-            assert (view.ctypes.data % 16) == (k * a.itemsize) % 16
+            assert a.size == 0 or (view.ctypes.data % 16) == (k * a.itemsize) % 16
             return buf, view
 
         keep = []
@@ -305,3 +305,44 @@ def test_emu_nvlink_carry_exchange(emu0, world, use_f32):
             if r < rows:
                 want[r] += carries[st, g]
         assert np.array_equal(y[st], want), (st, cuts.tolist())
+
+
+def test_emu_fuzz_small_matrices(emu0, orc):
+    """400 random small matrices (empty rows, single long rows, constant rows, sparse patterns),
+    random base-pointer misalignment, both value types; shipped kernel, variant 3 and the fused
+    single-launch path.  Small-integer inputs make the result exact in any summation order, so the
+    comparison with SpmvGold (cpu_spmv.cpp:257-277) is bit for bit."""
+    rng = np.random.default_rng(20261017)
+    for it in range(400):
+        dt = (np.float64, np.float32)[it & 1]
+        rows = int(rng.integers(1, 400)) if rng.random() < 0.8 else int(rng.integers(400, 2500))
+        cols = int(rng.integers(1, 200))
+        mode = int(rng.integers(0, 5))
+        if mode == 0:
+            lens = rng.integers(0, min(cols, 4) + 1, rows)
+        elif mode == 1:
+            lens = rng.poisson(rng.uniform(0.1, 12), rows)
+        elif mode == 2:
+            lens = np.zeros(rows, np.int64)
+            for _ in range(int(rng.integers(1, 4))):
+                lens[rng.integers(rows)] = rng.integers(0, cols + 1)
+        elif mode == 3:
+            lens = np.full(rows, rng.integers(0, min(cols, 16) + 1))
+        else:
+            lens = (rng.random(rows) < rng.uniform(0.05, 0.9)) * rng.integers(1, min(cols, 30) + 1, rows)
+        lens = np.minimum(lens, cols).astype(np.int64)
+        ro = np.zeros(rows + 1, np.int32)
+        ro[1:] = np.cumsum(lens)
+        nnz = int(ro[-1])
+        col = np.empty(nnz, np.int32)
+        for r in np.nonzero(lens)[0]:
+            col[ro[r]:ro[r + 1]] = np.sort(rng.choice(cols, lens[r], replace=False))
+        val = rng.integers(1, 8, nnz).astype(dt)
+        x = rng.integers(1, 8, cols).astype(dt)
+        want = orc.spmv_gold(ro, col, val.astype(np.float64), x.astype(np.float64)).astype(dt)
+        per16 = 16 // np.dtype(dt).itemsize
+        mis = (int(rng.integers(per16)), int(rng.integers(4)), int(rng.integers(4)))
+        variant = 3 if rng.random() < 0.4 else 2
+        fused = variant == 2 and rng.random() < 0.3
+        got = emu0.csrmv(ro, col, val, x, misalign=mis, variant=variant, fused=fused)
+        assert np.array_equal(got, want), (it, rows, cols, nnz, mode, mis, variant, fused)
