@@ -135,6 +135,13 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t 
 #ifndef MSPMV_GATHER_FLAVOUR
 #define MSPMV_GATHER_FLAVOUR 5
 #endif
+// Experiment (off): gathers of scattered columns bypass L1 altogether (ld.global.cg, cached in L2
+// only) instead of ld.global.nc.L1::no_allocate.  The measured gather ceiling depends on how much
+// L1 is left for misses in flight (profiles/microbench_r01.txt); loads that never allocate a line
+// may not be subject to it.
+#ifndef MSPMV_GATHER_SCATTERED_CG
+#define MSPMV_GATHER_SCATTERED_CG 0
+#endif
 __device__ __forceinline__ uint64_t l2_policy_evict_last()
 {
     uint64_t pol;
@@ -146,6 +153,8 @@ __device__ __forceinline__ float ld_gather(const float* p, uint64_t pol)
     float v;
 #if MSPMV_GATHER_FLAVOUR == 4
     asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+#elif MSPMV_GATHER_SCATTERED_CG
+    asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
 #else
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
 #endif
@@ -156,6 +165,8 @@ __device__ __forceinline__ double ld_gather(const double* p, uint64_t pol)
     double v;
 #if MSPMV_GATHER_FLAVOUR == 4
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+#elif MSPMV_GATHER_SCATTERED_CG
+    asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
 #else
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
 #endif

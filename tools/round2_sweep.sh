@@ -47,6 +47,8 @@ for W in uniform_1m_64 powerlaw_2m banded_10m uniform_1m_64_local; do
     run "shipped"                 -- --workload $W
     run "tile_variant=3"          -- --workload $W --option tile_variant=3
     run "tile_variant=3 carve 56" MSPMV_TILE_CARVEOUT=56 -- --workload $W --option tile_variant=3
+    run "shipped kernel, .cg scattered gathers" MSPMV_LIB=$V/libmergespmv_gathercg.so -- --workload $W
+    run "tile_variant=3, .cg scattered gathers" MSPMV_LIB=$V/libmergespmv_gathercg.so -- --workload $W --option tile_variant=3
     run "tile_variant=3, popcount prefix" MSPMV_LIB=$V/libmergespmv_v3popc.so -- --workload $W --option tile_variant=3
     run "tile_variant=3, shuffle-flag scan" MSPMV_LIB=$V/libmergespmv_v3shflscan.so -- --workload $W --option tile_variant=3
     run "tile_variant=3, 48 registers"  MSPMV_LIB=$V/libmergespmv_v3regs48.so -- --workload $W --option tile_variant=3
