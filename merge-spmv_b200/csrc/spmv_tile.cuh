@@ -52,7 +52,10 @@ struct TileCfg {
     static constexpr int FIX = 256;               // carries per fix-up block
     static constexpr int LOCAL_SPAN = 32768;      // a warp whose columns span fewer elements than this lets its gathers allocate in L1
     static constexpr int ROWCAP = 384;            // row offsets staged in shared memory; tiles with more read them from L2
-    static_assert(TILE % 32 == 0 && (IPT & 1) == 1 && IPT < 32, "bitmap layout");
+    // Odd IPT keeps the thread-blocked shared-memory reads conflict-free where threads hold no row end
+    // (long rows); where every thread holds exactly one (rows of ~IPT items, e.g. the banded config)
+    // an even IPT does (tools/lsu_model.py).  Both are legal; the bitmap layout only needs IPT < 32.
+    static_assert(TILE % 32 == 0 && IPT >= 2 && IPT < 32, "bitmap layout");
 };
 
 // ---- step 1: tile boundary coordinates (DeviceSpmvSearchKernel, dispatch_spmv_orig.cuh:104-143)

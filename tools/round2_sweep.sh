@@ -49,6 +49,10 @@ for W in uniform_1m_64 powerlaw_2m banded_10m uniform_1m_64_local; do
     run "tile_variant=3 carve 56" MSPMV_TILE_CARVEOUT=56 -- --workload $W --option tile_variant=3
     run "shipped kernel, .cg scattered gathers" MSPMV_LIB=$V/libmergespmv_gathercg.so -- --workload $W
     run "tile_variant=3, .cg scattered gathers" MSPMV_LIB=$V/libmergespmv_gathercg.so -- --workload $W --option tile_variant=3
+    for I in ipt8_12 ipt10_14 ipt11_15; do
+        run "shipped kernel, $I" MSPMV_LIB=$V/libmergespmv_$I.so -- --workload $W
+        run "tile_variant=3, $I" MSPMV_LIB=$V/libmergespmv_$I.so -- --workload $W --option tile_variant=3
+    done
     run "tile_variant=3, popcount prefix" MSPMV_LIB=$V/libmergespmv_v3popc.so -- --workload $W --option tile_variant=3
     run "tile_variant=3, shuffle-flag scan" MSPMV_LIB=$V/libmergespmv_v3shflscan.so -- --workload $W --option tile_variant=3
     run "tile_variant=3, 48 registers"  MSPMV_LIB=$V/libmergespmv_v3regs48.so -- --workload $W --option tile_variant=3
