@@ -143,6 +143,51 @@ static float test_cusparse_spmv(const Csr<V>& a, const V* y_in, const V* y_ref, 
     return elapsed / timing_iterations;
 }
 
+// Second yardstick: the toolkit's own cub::DeviceSpmv::CsrMV (host/cub_comparator.cu), y = A*x only
+extern "C" int toolkit_cub_csrmv_f64(void*, size_t*, const double*, const int*, const int*, const double*, double*, int,
+                                     int, int, cudaStream_t);
+extern "C" int toolkit_cub_csrmv_f32(void*, size_t*, const float*, const int*, const int*, const float*, float*, int,
+                                     int, int, cudaStream_t);
+static int toolkit_cub_csrmv(void* t, size_t* b, const double* v, const int* ro, const int* ci, const double* x,
+                             double* y, int r, int c, int n)
+{
+    return toolkit_cub_csrmv_f64(t, b, v, ro, ci, x, y, r, c, n, 0);
+}
+static int toolkit_cub_csrmv(void* t, size_t* b, const float* v, const int* ro, const int* ci, const float* x, float* y,
+                             int r, int c, int n)
+{
+    return toolkit_cub_csrmv_f32(t, b, v, ro, ci, x, y, r, c, n, 0);
+}
+
+template <typename V>
+static float test_toolkit_cub(const Csr<V>& a, const V* y_in, const V* y_ref, DeviceProblem<V>& p, int timing_iterations,
+                              float& setup_ms)
+{
+    setup_ms = 0.0f;
+    size_t temp_bytes = 0;
+    void* d_temp = nullptr;
+    auto call = [&](void* temp) {
+        return (cudaError_t)toolkit_cub_csrmv(temp, &temp_bytes, p.d_values, p.d_row_offsets, p.d_col, p.d_x, p.d_y,
+                                              a.num_rows, a.num_cols, a.num_nonzeros);
+    };
+    CUDA_EXIT(call(nullptr));
+    CUDA_EXIT(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
+    CUDA_EXIT(cudaMemcpy(p.d_y, y_in, sizeof(V) * a.num_rows, cudaMemcpyHostToDevice));
+    CUDA_EXIT(call(d_temp));
+    if (!g_quiet) {
+        int compare = compare_device(y_ref, p.d_y, a.num_rows);
+        std::printf("\t%s\n", compare ? "FAIL" : "PASS");
+        std::fflush(stdout);
+    }
+    GpuTimer timer;
+    timer.Start();
+    for (int it = 0; it < timing_iterations; ++it) CUDA_EXIT(call(d_temp));
+    timer.Stop();
+    float elapsed = timer.ElapsedMillis();
+    CUDA_EXIT(cudaFree(d_temp));
+    return elapsed / timing_iterations;
+}
+
 template <typename V>
 static void display_perf(float device_giga_bandwidth, double setup_ms, double avg_ms, const Csr<V>& a)
 {
@@ -215,6 +260,17 @@ static void run_tests(const CommandLineArgs& args, V alpha, V beta, int timing_i
         avg_ms = test_cusparse_spmv(a, y_in.data(), y_ref.data(), p, alpha, beta, timing_iterations, setup_ms);
         display_perf(device_giga_bandwidth, setup_ms, avg_ms, a);
     }
+    if (args.CheckCmdLineFlag("cub")) {
+        if (alpha != V(1) || beta != V(0)) {
+            std::fprintf(stderr, "--cub: the toolkit's cub::DeviceSpmv computes y = A*x only; skipped\n");
+        } else {
+            if (!g_quiet) std::printf("\n\n");
+            std::printf("CUDA toolkit cub::DeviceSpmv CsrMV, ");
+            std::fflush(stdout);
+            avg_ms = test_toolkit_cub(a, y_in.data(), y_ref.data(), p, timing_iterations, setup_ms);
+            display_perf(device_giga_bandwidth, setup_ms, avg_ms, a);
+        }
+    }
     cudaFree(p.d_values);
     cudaFree(p.d_row_offsets);
     cudaFree(p.d_col);
@@ -227,7 +283,7 @@ int main(int argc, char** argv)
     CommandLineArgs args(argc, argv);
     if (args.CheckCmdLineFlag("help")) {
         std::printf("%s [--device=<device-id>] [--quiet] [--v] [--i=<timing iterations>] [--fp32] "
-                    "[--alpha=<alpha scalar (default: 1.0)>] [--beta=<beta scalar (default: 0.0)>] [--cusparse]\n"
+                    "[--alpha=<alpha scalar (default: 1.0)>] [--beta=<beta scalar (default: 0.0)>] [--cusparse] [--cub]\n"
                     "\t--mtx=<matrix market file>\n\t--dense=<cols> [--size=<nnz>]\n\t--grid2d=<width>\n\t--grid3d=<width>\n"
                     "\t--wheel=<spokes>\n\t--uniform=<nnz per row> [--rows=] [--cols=]\n"
                     "\t--powerlaw=<max row length> [--rows=] [--cols=] [--nnz=]\n\t--banded=<half bandwidth> [--rows=]\n"

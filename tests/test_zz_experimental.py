@@ -9,7 +9,8 @@ Current subjects:
   * small_fused_tiles  -- the single-launch path for small matrices (spmv_tile_fused_kernel);
   * tile_variant=3     -- thread-blocked gathers with the products in registers (spmv_tile3_kernel):
                           same floating-point operations in the same order, so bit-identical to the
-                          shipped kernel.
+                          shipped kernel;
+  * gpu_spmv --cub     -- the toolkit's cub::DeviceSpmv as a second same-box comparator.
 """
 import os
 
@@ -140,3 +141,17 @@ def test_variant3_bit_identical_full_size(variant3, name):
     y3 = ms.csrmv(m.row_offsets, m.col, m.val, x)
     torch.cuda.synchronize()
     assert torch.equal(y2, y3)
+
+
+def test_driver_toolkit_cub_comparator():
+    """gpu_spmv --cub: the CUDA toolkit's own cub::DeviceSpmv::CsrMV (the maintained descendant of the
+    reference's kernels) must PASS the driver's self-check next to the merge CsrMV."""
+    import subprocess
+
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "merge-spmv_b200", "gpu_spmv")
+    for flags in (["--uniform=64", "--rows=65536", "--values=random", "--randx"], ["--banded=3", "--rows=200000"],
+                  ["--powerlaw=20000", "--rows=50000", "--nnz=3000000", "--fp32"]):
+        r = subprocess.run([exe, "--i=20", "--cub", "--cusparse"] + flags, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert "CUDA toolkit cub::DeviceSpmv CsrMV" in r.stdout and "FAIL" not in r.stdout and r.stdout.count("PASS") == 3, r.stdout

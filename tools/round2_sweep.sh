@@ -2,7 +2,7 @@
 # First GPU call of the next round: parity of the opt-in variants, then one timing table of every
 # variant on the four single-GPU workloads.  Everything lands in gpurun_out/ (merged back by gpurun).
 #
-#   gpurun --timeout 1500 -- 'bash tools/round2_sweep.sh'
+#   gpurun --timeout 2700 -- 'bash tools/round2_sweep.sh'     (about 60 bench.py runs of ~25 s each)
 #
 # Variants (all off by default; kernel logic already covered on CPU by tests/test_kernel_emu.py):
 #   tile_variant=3          thread-blocked gathers, products in registers (csrc/spmv_tile3.cuh)
@@ -62,6 +62,13 @@ run "shipped (3 launches)"        -- --workload cpu_uniform_16k --steps 2000
 run "small_fused_tiles=4096"      -- --workload cpu_uniform_16k --steps 2000 --option small_fused_tiles=4096
 run "shipped, eager launches"     -- --workload cpu_uniform_16k --steps 2000 --graph off
 run "fused, eager launches"       -- --workload cpu_uniform_16k --steps 2000 --graph off --option small_fused_tiles=4096
+
+echo "== same-box comparators through the C++ driver (merge CsrMV | cusparseSpMV ALG2 | toolkit cub::DeviceSpmv)" | tee -a "$OUT/sweep_r02.txt"
+D=merge-spmv_b200/gpu_spmv
+( timeout 600 $D --uniform=64 --rows=1048576 --values=random --randx --cusparse --cub
+  timeout 600 $D --powerlaw=1000000 --rows=2000000 --nnz=200000000 --fp32 --values=random --randx --cusparse --cub
+  timeout 600 $D --banded=3 --rows=10000000 --values=random --randx --cusparse --cub ) 2>&1 \
+    | grep -E "CsrMV|SpMV|PASS|FAIL|avg ms" | tee -a "$OUT/sweep_r02.txt" | tail -40
 
 # multi-GPU (run this script under `gpurun --gpus 2`): NCCL all_gather + fold vs the NVLink peer-memory
 # exchange kernel, and the solver-style step with the y all_gather
