@@ -57,6 +57,13 @@ for W in uniform_1m_64 powerlaw_2m banded_10m uniform_1m_64_local; do
     run "tile_variant=3, shuffle-flag scan" MSPMV_LIB=$V/libmergespmv_v3shflscan.so -- --workload $W --option tile_variant=3
     run "tile_variant=3, 48 registers"  MSPMV_LIB=$V/libmergespmv_v3regs48.so -- --workload $W --option tile_variant=3
 done
+echo "== shared-memory carve-out (L1 left for gather misses in flight) on the random-column workloads" | tee -a "$OUT/sweep_r02.txt"
+for W in uniform_1m_64 powerlaw_2m; do
+    for C in 50 56 62 85; do
+        run "shipped, carve-out $C %"        MSPMV_TILE_CARVEOUT=$C -- --workload $W
+        run "tile_variant=3, carve-out $C %" MSPMV_TILE_CARVEOUT=$C -- --workload $W --option tile_variant=3
+    done
+done
 echo "== small matrices (config 1 shape): launch-latency-bound" | tee -a "$OUT/sweep_r02.txt"
 run "shipped (3 launches)"        -- --workload cpu_uniform_16k --steps 2000
 run "small_fused_tiles=4096"      -- --workload cpu_uniform_16k --steps 2000 --option small_fused_tiles=4096
