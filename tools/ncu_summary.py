@@ -14,9 +14,11 @@ METRICS = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__warps_active.avg.pct_of_peak_sustained_active",
-    "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
+    "launch__registers_per_thread", "launch__shared_mem_config_size", "launch__shared_mem_per_block_static",
+    "launch__occupancy_limit_shared_mem",
     "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
     "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
     "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
