@@ -369,6 +369,7 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "kernel": ("spmv_stream_kernel" if (args.engine or "tile") == "stream" else
                            "spmv_tile3_kernel" if options.get("tile_variant") == 3 else "spmv_tile_kernel"),
                 "algorithmic_bytes_per_launch": shard_bytes,
+                "frac_of_nominal_8000_gbs": achieved / 8000.0,  # BASELINE.md section 2 also asks for the nominal figure
                 "note": "duration = whole step (search + tile + carry fix-up kernels; the tile kernel is 94.7% of it, profiles/launches_r01.csv), CUDA events"}
 
     if kind in ("uniform", "powerlaw"):
