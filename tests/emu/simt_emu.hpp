@@ -59,6 +59,8 @@ struct State {
     std::function<void()> body;
     char* stacks = nullptr;
     uint64_t collectives = 0, block_barriers = 0;  // statistics (per launch)
+    int schedule = 0;                               // see run_block()
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
 };
 inline State& S()
 {
@@ -105,10 +107,22 @@ inline void run_block(int nthreads)
         makecontext(&l.ctx, trampoline, 0);
         l.done = false;
     }
+    // Resume order of the threads within a pass: 0 = ascending, 1 = descending, 2 = a fresh pseudo-random
+    // permutation every pass (set_schedule()).  Results of a correctly synchronised kernel do not depend
+    // on it; a read that is not ordered after its write by a barrier shows up as a difference.
     int remaining = nthreads;
+    std::vector<int> order(nthreads);
+    for (int t = 0; t < nthreads; ++t) order[t] = t;
     while (remaining) {
         s.progress = false;
-        for (int t = 0; t < nthreads; ++t) {
+        if (s.schedule == 2) {
+            for (int i = nthreads - 1; i > 0; --i) {
+                s.rng = s.rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[i], order[(int)((s.rng >> 33) % (uint64_t)(i + 1))]);
+            }
+        }
+        for (int k = 0; k < nthreads; ++k) {
+            const int t = s.schedule == 1 ? nthreads - 1 - k : order[k];
             Lane& l = s.lanes[t];
             if (l.done) continue;
             s.cur = t;
@@ -122,6 +136,8 @@ inline void run_block(int nthreads)
         }
     }
 }
+
+inline void set_schedule(int mode) { S().schedule = mode; }
 
 // kernel<<<grid, block>>>(args...)  ==  emu::launch(grid, block, [&] { kernel(args...); })
 template <typename F>

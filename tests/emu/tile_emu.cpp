@@ -146,6 +146,9 @@ int emu_exchange_f64(int world, int steps, const int* cuts, const int* carry_row
     return 0;
 }
 
+// thread resume order inside a block: 0 ascending, 1 descending, 2 random per pass
+void emu_set_schedule(int mode) { emu::set_schedule(mode); }
+
 // coordinates of arbitrary diagonals through the device search routine (merge_common.cuh)
 int emu_merge_path_search(const int* ro, int rows, int nnz, const int* diagonals, int n, int* coords)
 {

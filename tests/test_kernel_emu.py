@@ -308,13 +308,18 @@ def test_emu_nvlink_carry_exchange(emu0, world, use_f32):
         assert np.array_equal(y[st], want), (st, cuts.tolist())
 
 
-def test_emu_fuzz_small_matrices(emu0, orc):
+@pytest.mark.parametrize("schedule", [0, 1, 2])
+def test_emu_fuzz_small_matrices(emu0, orc, schedule):
     """400 random small matrices (empty rows, single long rows, constant rows, sparse patterns),
     random base-pointer misalignment, both value types; shipped kernel, variant 3 and the fused
     single-launch path.  Small-integer inputs make the result exact in any summation order, so the
     comparison with SpmvGold (cpu_spmv.cpp:257-277) is bit for bit."""
-    rng = np.random.default_rng(20261017)
-    for it in range(400):
+    # schedule: order in which the interpreter resumes the threads of a block (ascending, descending,
+    # random per pass) -- a kernel whose shared-memory reads are properly ordered after the writes by
+    # barriers gives the same bits under all of them
+    emu0.lib.emu_set_schedule(schedule)
+    rng = np.random.default_rng(20261017 + schedule)
+    for it in range(400 if schedule == 0 else 200):
         dt = (np.float64, np.float32)[it & 1]
         rows = int(rng.integers(1, 400)) if rng.random() < 0.8 else int(rng.integers(400, 2500))
         cols = int(rng.integers(1, 200))
@@ -346,4 +351,5 @@ def test_emu_fuzz_small_matrices(emu0, orc):
         variant = 3 if rng.random() < 0.4 else 2
         fused = variant == 2 and rng.random() < 0.3
         got = emu0.csrmv(ro, col, val, x, misalign=mis, variant=variant, fused=fused)
-        assert np.array_equal(got, want), (it, rows, cols, nnz, mode, mis, variant, fused)
+        assert np.array_equal(got, want), (it, rows, cols, nnz, mode, mis, variant, fused, schedule)
+    emu0.lib.emu_set_schedule(0)
