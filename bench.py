@@ -247,6 +247,10 @@ def main():
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
                     help="N>1: how the carries travel -- nccl: one all_gather + fold kernel (default); p2p: one kernel "
                          "per rank storing into the peers' symmetric memory over NVLink (csrc/carry_exchange.cuh)")
+    ap.add_argument("--e2e-pipeline", action="store_true",
+                    help="N>1: overlap the host->device copy of x, the sharded product and the device->host copy of the "
+                         "y slice over three streams and three buffer slots (what mspmv_session_apply_many does at N=1); "
+                         "default: one step after the other")
     ap.add_argument("--gather-y", action="store_true",
                     help="N>1: include the all_gather of the y slices in every step (solver-style: the whole y "
                          "on every rank, ready to be the next x)")
@@ -411,6 +415,48 @@ def main():
                    "api": "mspmv_session_apply_many (pinned host x in, host y out, 3-stage pipeline)",
                    "unpipelined_ms_per_step": single_ms, "matrix_upload_ms": setup_ms,
                    "matrix_upload_bytes": int(nnz * (vb + 4) + (rows + 1) * 4)}
+        elif args.e2e_pipeline:
+            # H2D(i+1) | product(i) | D2H(i-1) on three streams over K slots; the collective runs on the
+            # compute stream like the kernels.  Same bytes per step as the sequential form below.
+            K = 3
+            xh = x.cpu().pin_memory()
+            s_h2d, s_comp, s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
+            xds = [torch.empty_like(x) for _ in range(K)]
+            yds = [torch.empty(shard.owned_rows, dtype=dt, device=dev) for _ in range(K)]
+            yhs = [torch.empty(shard.owned_rows, dtype=dt).pin_memory() for _ in range(K)]
+            ev_x = [torch.cuda.Event() for _ in range(K)]
+            ev_k = [torch.cuda.Event() for _ in range(K)]
+            ev_y = [torch.cuda.Event() for _ in range(K)]
+
+            def run_pipelined(n):
+                for i in range(n):
+                    sl = i % K
+                    with torch.cuda.stream(s_h2d):
+                        if i >= K:
+                            s_h2d.wait_event(ev_k[sl])   # the product that read this x slot is done
+                        xds[sl].copy_(xh, non_blocking=True)
+                        ev_x[sl].record(s_h2d)
+                    with torch.cuda.stream(s_comp):
+                        s_comp.wait_event(ev_x[sl])
+                        if i >= K:
+                            s_comp.wait_event(ev_y[sl])  # the copy that drained this y slot is done
+                        yds[sl].copy_(op(xds[sl]))
+                        ev_k[sl].record(s_comp)
+                    with torch.cuda.stream(s_d2h):
+                        s_d2h.wait_event(ev_k[sl])
+                        yhs[sl].copy_(yds[sl], non_blocking=True)
+                        ev_y[sl].record(s_d2h)
+                for st in (s_h2d, s_comp, s_d2h):
+                    st.synchronize()
+
+            torch.cuda.synchronize()
+            run_pipelined(K)  # warm
+            barrier()
+            t0 = time.perf_counter()
+            run_pipelined(n_e2e)
+            barrier()
+            dt_s = time.perf_counter() - t0
+            assert torch.equal(yhs[(n_e2e - 1) % K].to(dev), y if not gather_y else y[shard.x0:shard.x1])
         else:
             xh = x.cpu().pin_memory()
             yh = torch.empty(shard.owned_rows, dtype=dt).pin_memory()
@@ -426,7 +472,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e = {"value": 2.0 * nnz * n_e2e / float(tt.item()) / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": cols * vb, "d2h_bytes_per_step": shard.owned_rows * vb,
-                   "steps": n_e2e, "api": "ShardedSpmv with pinned host x / y per rank"}
+                   "steps": n_e2e, "api": "ShardedSpmv with pinned host x / y per rank"
+                                          + (", three-stream pipeline" if args.e2e_pipeline else ", sequential")}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------
     cpu = None

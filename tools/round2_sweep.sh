@@ -91,6 +91,11 @@ if [ "$NGPU" -ge 2 ]; then
     line=$(timeout 900 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node "$NGPU" --master-addr 127.0.0.1 \
            --master-port 29518 bench.py --gpus "$NGPU" --steps "$STEPS" --warmup 10 --no-e2e --gather-y 2>/dev/null | tail -1)
     echo "gather-y: $line" | cut -c1-400 | tee -a "$OUT/sweep_r02.txt"
+    for P in "" "--e2e-pipeline"; do
+        line=$(timeout 900 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node "$NGPU" --master-addr 127.0.0.1 \
+               --master-port 29519 bench.py --gpus "$NGPU" --steps 100 --warmup 10 $P 2>/dev/null | tail -1)
+        echo "e2e ${P:-sequential}: $($PY -c "import json,sys; d=json.loads(sys.argv[1]); print(d['e2e'])" "$line" 2>/dev/null)" | tee -a "$OUT/sweep_r02.txt"
+    done
 fi
 
 # one ncu capture of the candidate kernel next to the shipped one (banded: the issue-bound case)
