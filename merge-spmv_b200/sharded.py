@@ -168,6 +168,16 @@ class ShardedSpmv:
         self._xhdl = symm_mem.rendezvous(self._xbuf, group.group_name)
         if self._xhdl.world_size != s.world or self._xhdl.rank != s.rank:
             raise _lib.MergeSpmvError("symmetric-memory group does not match the shard layout")
+        # Address of the buffer in every rank's mapping.  The handle reports the base of each rank's
+        # symmetric allocation; the tensor may sit at an offset inside it (pool allocators), which is
+        # the same on every rank.  Check the arithmetic against the one address we know: our own.
+        bases = [int(p) for p in self._xhdl.buffer_ptrs]
+        off = int(getattr(self._xhdl, "offset", 0) or 0)
+        if bases[s.rank] + off != self._xbuf.data_ptr():
+            off = self._xbuf.data_ptr() - bases[s.rank]
+            if off < 0 or off + nbytes > int(self._xhdl.buffer_size):
+                raise _lib.MergeSpmvError("cannot locate the exchange buffer inside the symmetric allocation")
+        self._peer_table = torch.tensor([b + off for b in bases], dtype=torch.int64, device=dev)
         torch.cuda.synchronize(dev)
         self._xhdl.barrier()  # every buffer is zero before anybody pushes
         self._epoch = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -178,7 +188,7 @@ class ShardedSpmv:
         fn = getattr(_lib.lib(), f"mspmv_exchange_carries_{sfx}")
         with torch.cuda.device(self.y_local.device):
             _lib.check(fn(_ptr(self.y_local), s.local_rows, s.x0, s.owned_rows, s.rows_global,
-                          _ptr(s.carry_rows), C.c_void_p(int(self._xhdl.buffer_ptrs_dev)), s.rank, s.world,
+                          _ptr(s.carry_rows), _ptr(self._peer_table), s.rank, s.world,
                           _ptr(self._epoch), _stream(None)), "exchange_carries")
 
     def capture(self, x, gather_y=False):
