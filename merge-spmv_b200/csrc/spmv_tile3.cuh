@@ -6,7 +6,9 @@
 // learns its start coordinate (bitmap + popcount prefix need only the row offsets), then reads ITS
 // OWN contiguous run of column indices and values from the staged tile, gathers x for them and
 // walks with the products in registers: no product store / reload, one shared-memory read per
-// operand, ~1/4 fewer instructions per merge item (SASS: profiles/sass_r01.txt).  The order of the
+// operand; the popcount prefix is replaced by the row owners scattering start rows, the warp scan
+// is ballot-driven.  ~1/6 fewer executed instructions per thread (profiles/sass_static_r01.txt,
+// tools/sass_lines.py) and ~9 % fewer LSU wavefronts per tile (tools/lsu_model.py).  The order of the
 // floating-point operations is unchanged, so the results are bit-identical to tile_body's.
 // Trade-off to be measured: the gathers issue after the prefix instead of right after the TMA wait,
 // and a warp's gathers cover 32*IPT consecutive nonzeros instead of 32.
