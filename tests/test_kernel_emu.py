@@ -29,6 +29,7 @@ VARIANTS = {
     "shipped": [],
     "prefix_shfl": ["-DMSPMV_PREFIX_SHFL"],
     "ipt_11_15": ["-DMSPMV_TILE_IPT=(sizeof(T)==8?11:15)"],
+    "ipt_7_11": ["-DMSPMV_TILE_IPT=(sizeof(T)==8?7:11)"],
     "ipt_8_12": ["-DMSPMV_TILE_IPT=(sizeof(T)==8?8:12)"],
     "v3_popcount_prefix": ["-DMSPMV_V3_XS_SCATTER=0", "-DMSPMV_V3_BALLOT_SCAN=0"],
 }

@@ -47,9 +47,7 @@ for W in uniform_1m_64 powerlaw_2m banded_10m uniform_1m_64_local; do
     run "shipped"                 -- --workload $W
     run "tile_variant=3"          -- --workload $W --option tile_variant=3
     run "tile_variant=3 carve 56" MSPMV_TILE_CARVEOUT=56 -- --workload $W --option tile_variant=3
-    run "shipped kernel, .cg scattered gathers" MSPMV_LIB=$V/libmergespmv_gathercg.so -- --workload $W
-    run "tile_variant=3, .cg scattered gathers" MSPMV_LIB=$V/libmergespmv_gathercg.so -- --workload $W --option tile_variant=3
-    for I in ipt8_12 ipt10_14 ipt11_15; do
+    for I in ipt7_11 ipt8_12 ipt10_14 ipt11_15; do
         run "shipped kernel, $I" MSPMV_LIB=$V/libmergespmv_$I.so -- --workload $W
         run "tile_variant=3, $I" MSPMV_LIB=$V/libmergespmv_$I.so -- --workload $W --option tile_variant=3
     done
@@ -62,6 +60,15 @@ for W in uniform_1m_64 powerlaw_2m; do
     for C in 50 56 62 85; do
         run "shipped, carve-out $C %"        MSPMV_TILE_CARVEOUT=$C -- --workload $W
         run "tile_variant=3, carve-out $C %" MSPMV_TILE_CARVEOUT=$C -- --workload $W --option tile_variant=3
+    done
+done
+# smaller tiles leave more of the 228 KB to L1: 7 / 11 items per thread are ~13 KB per block, so 9 blocks fit
+# a 132 KB shared-memory configuration (the gather ceiling is 275 G/s there, 252 at 164 KB, 127 at 196 KB:
+# profiles/microbench_r01.txt)
+for W in uniform_1m_64 powerlaw_2m; do
+    for C in 50 56 62; do
+        run "shipped, ipt7_11, carve-out $C %"        MSPMV_LIB=$V/libmergespmv_ipt7_11.so MSPMV_TILE_CARVEOUT=$C -- --workload $W
+        run "tile_variant=3, ipt7_11, carve-out $C %" MSPMV_LIB=$V/libmergespmv_ipt7_11.so MSPMV_TILE_CARVEOUT=$C -- --workload $W --option tile_variant=3
     done
 done
 echo "== small matrices (config 1 shape): launch-latency-bound" | tee -a "$OUT/sweep_r02.txt"
