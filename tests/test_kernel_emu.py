@@ -354,3 +354,32 @@ def test_emu_fuzz_small_matrices(emu0, orc, schedule):
         got = emu0.csrmv(ro, col, val, x, misalign=mis, variant=variant, fused=fused)
         assert np.array_equal(got, want), (it, rows, cols, nnz, mode, mis, variant, fused, schedule)
     emu0.lib.emu_set_schedule(0)
+
+
+@pytest.mark.parametrize("dt,tile", [(np.float64, 1152), (np.float32, 1664)])
+def test_emu_tile_boundary_cases(emu0, orc, dt, tile):
+    """Structures built around the tile size: row ends on the last / first item of a tile, two ends
+    across a boundary, tiles made only of empty rows (more row ends than ROWCAP), a row spanning
+    several tiles, trailing empty rows, degenerate sizes -- shipped kernel, variant 3 and the fused
+    launch, aligned and misaligned bases, bit-exact against SpmvGold on small-integer inputs."""
+    cases = [
+        ([tile - 1] * 3, 2000), ([tile] * 3, 2000), ([tile - 2, 0] * 3, 2000), ([0] * (tile * 2), 5),
+        ([0] * (tile * 2 + 1), 5), ([1] * (tile // 2 * 3), 7), ([0] * 500 + [1900] + [0] * 700, 2000),
+        ([3] * 100 + [0] * tile, 10), ([tile * 3 + 5], 5000), ([2] * 5, 3), ([0], 1), (list(np.arange(60) % 9), 9),
+    ]
+    rng = np.random.default_rng(3)
+    for lens, cols in cases:
+        lens = np.asarray(lens, np.int64)
+        ro = np.zeros(lens.size + 1, np.int32)
+        ro[1:] = np.cumsum(lens)
+        nnz = int(ro[-1])
+        col = np.empty(nnz, np.int32)
+        for r in np.nonzero(lens)[0]:
+            col[ro[r]:ro[r + 1]] = np.sort(rng.choice(cols, lens[r], replace=False))
+        val = rng.integers(1, 5, nnz).astype(dt)
+        x = rng.integers(1, 5, cols).astype(dt)
+        want = orc.spmv_gold(ro, col, val.astype(np.float64), x.astype(np.float64)).astype(dt)
+        for variant, fused in ((2, False), (3, False), (2, True)):
+            for mis in ((0, 0, 0), (1, 3, 1)):
+                got = emu0.csrmv(ro, col, val, x, misalign=mis, variant=variant, fused=fused)
+                assert np.array_equal(got, want), (lens.size, nnz, variant, fused, mis)
