@@ -111,3 +111,22 @@ def test_default_kernels_are_the_measured_ones():
     now = mod.fingerprint(os.path.join(ROOT, "merge-spmv_b200", "libmergespmv.so"))
     changed = [k for k, v in measured.items() if now.get(k) != v]
     assert not changed, f"kernels differ from the measured build: {changed}"
+
+
+def test_sass_tools_smoke():
+    """tools/sass_lines.py maps the SASS of a kernel back to source lines (the library is built with
+    -lineinfo): the shipped tile kernel must show TMA bulk copies and attribute instructions to
+    spmv_tile.cuh."""
+    import shutil
+    import subprocess
+    import sys
+
+    if shutil.which("nvdisasm") is None or shutil.which("cuobjdump") is None:
+        pytest.skip("CUDA binary utilities not on PATH")
+    tool = os.path.join(ROOT, "tools", "sass_lines.py")
+    by_file = subprocess.run([sys.executable, tool, "spmv_tile_kernelIdLb0", "--by-file"], capture_output=True, text=True,
+                             check=True).stdout
+    assert "spmv_tile.cuh" in by_file and "tma_stage.cuh" in by_file
+    ops = subprocess.run([sys.executable, tool, "spmv_tile_kernelIdLb0", "--ops"], capture_output=True, text=True,
+                         check=True).stdout
+    assert "UBLKCP" in ops and "SYNCS" in ops, "TMA bulk copy / mbarrier instructions missing from the tile kernel"
