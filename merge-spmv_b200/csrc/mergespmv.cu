@@ -216,12 +216,12 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     dim3 grid(p.num_tiles), block(C::THREADS);
     if (p.num_tiles <= small_fused_tiles()) {
         // one launch: every block searches its own coordinates, the last block folds the carries
-        static bool fused_configured[64] = {};
+        static std::atomic<bool> fused_configured[64];  // per device; a benign race only repeats the call
         int dev = 0;
         cudaGetDevice(&dev);
-        if (!fused_configured[dev & 63]) {
+        if (!fused_configured[dev & 63].load(std::memory_order_relaxed)) {
             cudaFuncSetAttribute(spmv_tile_fused_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, 70);
-            fused_configured[dev & 63] = true;
+            fused_configured[dev & 63].store(true, std::memory_order_relaxed);
         }
         if (p.num_tiles > 1) MSPMV_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
         spmv_tile_fused_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, carry_rows,
@@ -238,27 +238,27 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
         // Shared-memory carve-out: the x gathers need L1 capacity for their misses in flight
         // (gather throughput halves once shared memory takes > ~160 KB of the 228 KB, see
         // profiles/microbench_r01.txt), so cap what the resident blocks may claim.
-        static bool configured[64] = {};
+        static std::atomic<bool> configured[64];  // per device; a benign race only repeats the call
         int dev = 0;
         cudaGetDevice(&dev);
-        if (!configured[dev & 63]) {
+        if (!configured[dev & 63].load(std::memory_order_relaxed)) {
             int pct = 70;  // ~160 KB shared, ~68 KB L1 (the driver default for this footprint; pinned so larger tiles keep it)
             if (const char* e = std::getenv("MSPMV_TILE_CARVEOUT")) pct = std::atoi(e);
             if (pct >= 0)
                 cudaFuncSetAttribute(spmv_tile_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            configured[dev & 63] = true;
+            configured[dev & 63].store(true, std::memory_order_relaxed);
         }
     }
     if (tile_variant() == 3) {
-        static bool v3_configured[64] = {};
+        static std::atomic<bool> v3_configured[64];  // per device; a benign race only repeats the call
         int dev = 0;
         cudaGetDevice(&dev);
-        if (!v3_configured[dev & 63]) {
+        if (!v3_configured[dev & 63].load(std::memory_order_relaxed)) {
             int pct = 70;
             if (const char* e = std::getenv("MSPMV_TILE_CARVEOUT")) pct = std::atoi(e);
             if (pct >= 0)
                 cudaFuncSetAttribute(spmv_tile3_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            v3_configured[dev & 63] = true;
+            v3_configured[dev & 63].store(true, std::memory_order_relaxed);
         }
         spmv_tile3_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
                                                                carry_vals, alpha, beta, num_rows, num_nonzeros,
