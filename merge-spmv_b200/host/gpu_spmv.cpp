@@ -188,6 +188,162 @@ static float test_toolkit_cub(const Csr<V>& a, const V* y_in, const V* y_ref, De
     return elapsed / timing_iterations;
 }
 
+// ---- one process, several GPUs (new surface: the reference is single-GPU, README.md:5) ---------
+// The matrix is cut into merge-path shards exactly like OmpMergeCsrmv cuts it between CPU threads
+// (cpu_spmv.cpp:311-321, mspmv_shard_partition); device g runs the unchanged single-GPU CsrMV on its
+// shard and then the NVLink carry exchange (mspmv_exchange_carries_*): it stores its carry into every
+// peer's exchange buffer -- plain cudaMalloc memory, peer access enabled, no NCCL -- waits for the
+// peers' flags and folds.  Launches are asynchronous, so one host thread can drive all devices; nothing
+// here blocks on a device before every device has been given its exchange kernel.
+static int csrmv_any(void* t, size_t* b, const double* v, const int* ro, const int* ci, const double* x, double* y, int r,
+                     int c, int n, cudaStream_t s)
+{
+    return mspmv_csrmv_f64(t, b, v, ro, ci, x, y, r, c, n, s, 0);
+}
+static int csrmv_any(void* t, size_t* b, const float* v, const int* ro, const int* ci, const float* x, float* y, int r,
+                     int c, int n, cudaStream_t s)
+{
+    return mspmv_csrmv_f32(t, b, v, ro, ci, x, y, r, c, n, s, 0);
+}
+static int exchange_any(double* y, int lr, int b, int n, int rg, const int* cr, void* const* pb, int rank, int p,
+                        unsigned long long* e, cudaStream_t s)
+{
+    return mspmv_exchange_carries_f64(y, lr, b, n, rg, cr, pb, rank, p, e, s);
+}
+static int exchange_any(float* y, int lr, int b, int n, int rg, const int* cr, void* const* pb, int rank, int p,
+                        unsigned long long* e, cudaStream_t s)
+{
+    return mspmv_exchange_carries_f32(y, lr, b, n, rg, cr, pb, rank, p, e, s);
+}
+
+template <typename V>
+static float test_merge_csrmv_multi(const Csr<V>& a, const V* x_host, const V* y_ref, int p, int timing_iterations,
+                                    float& setup_ms)
+{
+    struct Dev {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        V *val = nullptr, *x = nullptr, *y = nullptr;
+        int *ro = nullptr, *col = nullptr, *carry_rows = nullptr;
+        void *temp = nullptr, *xbuf = nullptr;
+        void** peers = nullptr;
+        unsigned long long* epoch = nullptr;
+        size_t temp_bytes = 0;
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0, local_rows = 0, owned = 0, nnz = 0;
+    };
+    std::vector<Dev> d(p);
+    std::vector<int> coords(2 * (p + 1));
+    mspmv_shard_partition(a.row_offsets.data(), a.num_rows, a.num_nonzeros, p, coords.data());
+    std::vector<int> carry_rows(p);
+    for (int g = 0; g < p; ++g) carry_rows[g] = coords[2 * (g + 1)];
+    const size_t xbytes = mspmv_exchange_buffer_bytes(p);
+    GpuTimer setup;
+    CUDA_EXIT(cudaSetDevice(0));
+    setup.Start();
+    for (int g = 0; g < p; ++g) {
+        Dev& D = d[g];
+        CUDA_EXIT(cudaSetDevice(g));
+        for (int h = 0; h < p; ++h) {
+            if (h == g) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(h, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else CUDA_EXIT(e);
+        }
+        CUDA_EXIT(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+        CUDA_EXIT(cudaEventCreate(&D.e0));
+        CUDA_EXIT(cudaEventCreate(&D.e1));
+        D.x0 = coords[2 * g], D.y0 = coords[2 * g + 1], D.x1 = coords[2 * g + 2], D.y1 = coords[2 * g + 3];
+        D.owned = D.x1 - D.x0, D.local_rows = D.owned + 1, D.nnz = D.y1 - D.y0;
+        std::vector<int> lro(D.local_rows + 1);
+        mspmv_shard_row_offsets(a.row_offsets.data(), D.x0, D.y0, D.x1, D.y1, lro.data());
+        CUDA_EXIT(cudaMalloc(&D.val, sizeof(V) * std::max(D.nnz, 1)));
+        CUDA_EXIT(cudaMalloc(&D.col, sizeof(int) * std::max(D.nnz, 1)));
+        CUDA_EXIT(cudaMalloc(&D.ro, sizeof(int) * (D.local_rows + 1)));
+        CUDA_EXIT(cudaMalloc(&D.x, sizeof(V) * a.num_cols));
+        CUDA_EXIT(cudaMalloc(&D.y, sizeof(V) * D.local_rows));
+        CUDA_EXIT(cudaMalloc(&D.carry_rows, sizeof(int) * p));
+        CUDA_EXIT(cudaMalloc(&D.xbuf, xbytes));
+        CUDA_EXIT(cudaMalloc(&D.peers, sizeof(void*) * p));
+        CUDA_EXIT(cudaMalloc(&D.epoch, sizeof(unsigned long long)));
+        CUDA_EXIT(cudaMemset(D.xbuf, 0, xbytes));
+        CUDA_EXIT(cudaMemset(D.epoch, 0, sizeof(unsigned long long)));
+        CUDA_EXIT(cudaMemcpy(D.val, a.values.data() + D.y0, sizeof(V) * D.nnz, cudaMemcpyHostToDevice));
+        CUDA_EXIT(cudaMemcpy(D.col, a.column_indices.data() + D.y0, sizeof(int) * D.nnz, cudaMemcpyHostToDevice));
+        CUDA_EXIT(cudaMemcpy(D.ro, lro.data(), sizeof(int) * (D.local_rows + 1), cudaMemcpyHostToDevice));
+        CUDA_EXIT(cudaMemcpy(D.x, x_host, sizeof(V) * a.num_cols, cudaMemcpyHostToDevice));
+        CUDA_EXIT(cudaMemcpy(D.carry_rows, carry_rows.data(), sizeof(int) * p, cudaMemcpyHostToDevice));
+        CUDA_EXIT((cudaError_t)csrmv_any(nullptr, &D.temp_bytes, (const V*)nullptr, nullptr, nullptr, (const V*)nullptr,
+                                         (V*)nullptr, D.local_rows, a.num_cols, D.nnz, nullptr));
+        CUDA_EXIT(cudaMalloc(&D.temp, D.temp_bytes));
+    }
+    std::vector<void*> table(p);
+    for (int g = 0; g < p; ++g) table[g] = d[g].xbuf;
+    for (int g = 0; g < p; ++g) {
+        CUDA_EXIT(cudaSetDevice(g));
+        CUDA_EXIT(cudaMemcpy(d[g].peers, table.data(), sizeof(void*) * p, cudaMemcpyHostToDevice));
+        CUDA_EXIT(cudaDeviceSynchronize());
+    }
+    CUDA_EXIT(cudaSetDevice(0));
+    setup.Stop();
+    setup_ms = setup.ElapsedMillis();
+
+    auto step = [&] {
+        for (int g = 0; g < p; ++g) {
+            Dev& D = d[g];
+            CUDA_EXIT(cudaSetDevice(g));
+            CUDA_EXIT((cudaError_t)csrmv_any(D.temp, &D.temp_bytes, D.val, D.ro, D.col, D.x, D.y, D.local_rows, a.num_cols,
+                                             D.nnz, D.stream));
+            CUDA_EXIT((cudaError_t)exchange_any(D.y, D.local_rows, D.x0, D.owned, a.num_rows, D.carry_rows, D.peers, g, p,
+                                                D.epoch, D.stream));
+        }
+    };
+    auto sync_all = [&] {
+        for (int g = 0; g < p; ++g) {
+            CUDA_EXIT(cudaSetDevice(g));
+            CUDA_EXIT(cudaStreamSynchronize(d[g].stream));
+        }
+    };
+    step();  // warm-up + check
+    sync_all();
+    if (!g_quiet) {
+        std::vector<V> y(a.num_rows);
+        for (int g = 0; g < p; ++g) {
+            CUDA_EXIT(cudaSetDevice(g));
+            if (d[g].owned > 0)
+                CUDA_EXIT(cudaMemcpy(y.data() + d[g].x0, d[g].y, sizeof(V) * d[g].owned, cudaMemcpyDeviceToHost));
+        }
+        int compare = compare_results(y.data(), y_ref, a.num_rows, true);
+        std::printf("\t%s\n", compare ? "FAIL" : "PASS");
+        std::fflush(stdout);
+    }
+    for (int g = 0; g < p; ++g) {
+        CUDA_EXIT(cudaSetDevice(g));
+        CUDA_EXIT(cudaEventRecord(d[g].e0, d[g].stream));
+    }
+    for (int it = 0; it < timing_iterations; ++it) step();
+    float elapsed = 0.f;
+    for (int g = 0; g < p; ++g) {
+        CUDA_EXIT(cudaSetDevice(g));
+        CUDA_EXIT(cudaEventRecord(d[g].e1, d[g].stream));
+    }
+    for (int g = 0; g < p; ++g) {  // device-side time, max over devices
+        CUDA_EXIT(cudaSetDevice(g));
+        CUDA_EXIT(cudaEventSynchronize(d[g].e1));
+        float ms = 0.f;
+        CUDA_EXIT(cudaEventElapsedTime(&ms, d[g].e0, d[g].e1));
+        elapsed = std::max(elapsed, ms);
+    }
+    for (int g = 0; g < p; ++g) {
+        Dev& D = d[g];
+        CUDA_EXIT(cudaSetDevice(g));
+        cudaFree(D.val), cudaFree(D.col), cudaFree(D.ro), cudaFree(D.x), cudaFree(D.y), cudaFree(D.carry_rows);
+        cudaFree(D.xbuf), cudaFree(D.peers), cudaFree(D.epoch), cudaFree(D.temp);
+        cudaEventDestroy(D.e0), cudaEventDestroy(D.e1), cudaStreamDestroy(D.stream);
+    }
+    CUDA_EXIT(cudaSetDevice(0));
+    return elapsed / timing_iterations;
+}
+
 template <typename V>
 static void display_perf(float device_giga_bandwidth, double setup_ms, double avg_ms, const Csr<V>& a)
 {
@@ -271,6 +427,21 @@ static void run_tests(const CommandLineArgs& args, V alpha, V beta, int timing_i
             display_perf(device_giga_bandwidth, setup_ms, avg_ms, a);
         }
     }
+    int gpus = 1;
+    args.GetCmdLineArgument("gpus", gpus);
+    if (gpus > 1) {
+        int have = 0;
+        CUDA_EXIT(cudaGetDeviceCount(&have));
+        if (alpha != V(1) || beta != V(0) || have < gpus) {
+            std::fprintf(stderr, "--gpus=%d: needs %d visible devices (have %d) and alpha=1, beta=0; skipped\n", gpus, gpus, have);
+        } else {
+            if (!g_quiet) std::printf("\n\n");
+            std::printf("Merge-based CsrMV x%d GPUs (merge-path shards, NVLink carry exchange), ", gpus);
+            std::fflush(stdout);
+            avg_ms = test_merge_csrmv_multi(a, x.data(), y_ref.data(), gpus, timing_iterations, setup_ms);
+            display_perf(device_giga_bandwidth * gpus, setup_ms, avg_ms, a);
+        }
+    }
     cudaFree(p.d_values);
     cudaFree(p.d_row_offsets);
     cudaFree(p.d_col);
@@ -283,7 +454,7 @@ int main(int argc, char** argv)
     CommandLineArgs args(argc, argv);
     if (args.CheckCmdLineFlag("help")) {
         std::printf("%s [--device=<device-id>] [--quiet] [--v] [--i=<timing iterations>] [--fp32] "
-                    "[--alpha=<alpha scalar (default: 1.0)>] [--beta=<beta scalar (default: 0.0)>] [--cusparse] [--cub]\n"
+                    "[--alpha=<alpha scalar (default: 1.0)>] [--beta=<beta scalar (default: 0.0)>] [--cusparse] [--cub] [--gpus=<n>]\n"
                     "\t--mtx=<matrix market file>\n\t--dense=<cols> [--size=<nnz>]\n\t--grid2d=<width>\n\t--grid3d=<width>\n"
                     "\t--wheel=<spokes>\n\t--uniform=<nnz per row> [--rows=] [--cols=]\n"
                     "\t--powerlaw=<max row length> [--rows=] [--cols=] [--nnz=]\n\t--banded=<half bandwidth> [--rows=]\n"

@@ -155,3 +155,20 @@ def test_driver_toolkit_cub_comparator():
         r = subprocess.run([exe, "--i=20", "--cub", "--cusparse"] + flags, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr
         assert "CUDA toolkit cub::DeviceSpmv CsrMV" in r.stdout and "FAIL" not in r.stdout and r.stdout.count("PASS") == 3, r.stdout
+
+
+def test_driver_single_process_multi_gpu():
+    """gpu_spmv --gpus=N: one process drives N devices, merge-path shards, carries exchanged by
+    mspmv_exchange_carries_* through peer memory (no NCCL); the gathered y must PASS the self-check."""
+    import subprocess
+
+    from conftest import ROOT
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    exe = os.path.join(ROOT, "merge-spmv_b200", "gpu_spmv")
+    for flags in (["--uniform=64", "--rows=262144", "--values=random", "--randx"],
+                  ["--powerlaw=200000", "--rows=100000", "--nnz=5000000", "--fp32"], ["--banded=3", "--rows=500000"]):
+        r = subprocess.run([exe, "--i=50", f"--gpus={min(n, 8)}"] + flags, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert "NVLink carry exchange" in r.stdout and "FAIL" not in r.stdout and r.stdout.count("PASS") == 2, r.stdout

@@ -98,6 +98,9 @@ if [ "$NGPU" -ge 2 ]; then
     line=$(timeout 900 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node "$NGPU" --master-addr 127.0.0.1 \
            --master-port 29518 bench.py --gpus "$NGPU" --steps "$STEPS" --warmup 10 --no-e2e --gather-y 2>/dev/null | tail -1)
     echo "gather-y: $line" | cut -c1-400 | tee -a "$OUT/sweep_r02.txt"
+    echo "-- C++ driver, one process driving $NGPU devices (peer-memory carry exchange, no NCCL)" | tee -a "$OUT/sweep_r02.txt"
+    timeout 900 merge-spmv_b200/gpu_spmv --uniform=64 --rows=$((1048576 * NGPU)) --cols=1048576 --values=random --randx --gpus=$NGPU 2>&1 \
+        | grep -E "CsrMV|PASS|FAIL|avg ms" | tee -a "$OUT/sweep_r02.txt"
     for P in "" "--e2e-pipeline"; do
         line=$(timeout 900 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node "$NGPU" --master-addr 127.0.0.1 \
                --master-port 29519 bench.py --gpus "$NGPU" --steps 100 --warmup 10 $P 2>/dev/null | tail -1)
