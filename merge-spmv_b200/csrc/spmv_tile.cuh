@@ -387,7 +387,7 @@ __global__ __launch_bounds__(256) void carry_fixup_block_kernel(const int* __res
     const int i = blockIdx.x * FIX + tid;
     const int row = i < n ? carry_rows[i] : INT_MAX;
     const T val = i < n ? carry_vals[i] : T(0);
-    const int prev_row = (i > 0 && tid > 0) ? carry_rows[i - 1] : -1;  // block-local run detection
+    const int prev_row = (tid > 0 && i < n) ? carry_rows[i - 1] : -1;  // block-local run detection; threads past n read nothing
     const int next_row = (i + 1 < n) ? carry_rows[i + 1] : INT_MAX;
 
     // inclusive segmented scan keyed by "row differs from the previous carry in this block"

@@ -109,8 +109,11 @@ def test_default_kernels_are_the_measured_ones():
     spec.loader.exec_module(mod)
     measured = json.load(open(os.path.join(ROOT, "profiles", "sass_fingerprint_r01.json")))
     now = mod.fingerprint(os.path.join(ROOT, "merge-spmv_b200", "libmergespmv.so"))
-    changed = [k for k, v in measured.items() if now.get(k) != v]
+    # kernels changed on purpose since the measurement, each with its reason
+    exceptions = json.load(open(os.path.join(ROOT, "profiles", "sass_fingerprint_exceptions.json")))
+    changed = [k for k, v in measured.items() if now.get(k) != v and not any(e in k for e in exceptions)]
     assert not changed, f"kernels differ from the measured build: {changed}"
+    assert all(k in now for k in measured), "a measured kernel is missing from the library"
 
 
 def test_sass_tools_smoke():
