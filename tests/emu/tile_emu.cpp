@@ -30,18 +30,21 @@ int run(const T* values, const int* row_offsets, const int* col, const T* x, T* 
     const int64_t merge_items = (int64_t)num_rows + num_nonzeros;
     const int num_tiles = (int)((merge_items + C::TILE - 1) / C::TILE);
     const int num_fix_blocks = (num_tiles + C::FIX - 1) / C::FIX;
-    // 16-byte aligned temporaries, uninitialised on purpose (the product's temp blob is)
-    std::vector<int4> coords_buf((size_t)(num_tiles + 1) / 2 + 2), cr_buf((size_t)num_tiles / 4 + 2),
-        c2r_buf((size_t)num_fix_blocks / 4 + 2);
-    std::vector<double> cv_buf((size_t)num_tiles + 2), c2v_buf((size_t)num_fix_blocks + 2);
-    int2* coords = reinterpret_cast<int2*>(coords_buf.data());
-    int* carry_rows = reinterpret_cast<int*>(cr_buf.data());
-    int* carry2_rows = reinterpret_cast<int*>(c2r_buf.data());
-    T* carry_vals = reinterpret_cast<T*>(cv_buf.data());
-    T* carry2_vals = reinterpret_cast<T*>(c2v_buf.data());
-    std::memset(coords_buf.data(), 0xEE, coords_buf.size() * sizeof(int4));
-    std::memset(cr_buf.data(), 0xEE, cr_buf.size() * sizeof(int4));
-    std::memset(cv_buf.data(), 0xEE, cv_buf.size() * sizeof(double));
+    // temporaries of exactly the size the dispatch carves out of the temp blob (so that AddressSanitizer
+    // sees any access past them), filled with garbage on purpose (the product's temp blob is uninitialised)
+    std::vector<int2> coords_buf((size_t)num_tiles + 1);
+    std::vector<int> cr_buf((size_t)num_tiles), c2r_buf((size_t)num_fix_blocks);
+    std::vector<T> cv_buf((size_t)num_tiles), c2v_buf((size_t)num_fix_blocks);
+    int2* coords = coords_buf.data();
+    int* carry_rows = cr_buf.data();
+    int* carry2_rows = c2r_buf.data();
+    T* carry_vals = cv_buf.data();
+    T* carry2_vals = c2v_buf.data();
+    std::memset(coords_buf.data(), 0xEE, coords_buf.size() * sizeof(int2));
+    std::memset(cr_buf.data(), 0xEE, cr_buf.size() * sizeof(int));
+    std::memset(cv_buf.data(), 0xEE, cv_buf.size() * sizeof(T));
+    std::memset(c2r_buf.data(), 0xEE, c2r_buf.size() * sizeof(int));
+    std::memset(c2v_buf.data(), 0xEE, c2v_buf.size() * sizeof(T));
     unsigned int ticket = 0xEEEEEEEEu;
 
     const int* row_end = row_offsets + 1;
