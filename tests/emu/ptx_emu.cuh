@@ -27,14 +27,19 @@ struct EmuBulkCopy {
     uint32_t bytes;
     uint64_t* bar;
 };
-inline std::vector<EmuBulkCopy>& emu_inflight()
+EMU_INTERNAL inline std::vector<EmuBulkCopy>& emu_inflight()
 {
     static std::vector<EmuBulkCopy> v;
     return v;
 }
-inline EmuMbar* emu_bar(uint64_t* bar) { return reinterpret_cast<EmuMbar*>(bar); }
+// the data movement of a bulk copy, visible to the sanitizers as ordinary writes of the thread that
+// completes the phase (ordered before the waiters by the release / acquire on the barrier)
+inline void emu_land_copy(void* dst, const void* src, uint32_t bytes) { std::memcpy(dst, src, bytes); }
+inline void emu_poison_copy(void* dst, uint32_t bytes) { std::memset(dst, 0xCD, bytes); }
 
-inline void emu_mbar_check_complete(uint64_t* bar)
+EMU_INTERNAL inline EmuMbar* emu_bar(uint64_t* bar) { return reinterpret_cast<EmuMbar*>(bar); }
+
+EMU_INTERNAL inline void emu_mbar_check_complete(uint64_t* bar)
 {
     EmuMbar* b = emu_bar(bar);
     if (b->pending != 0 || b->tx != 0) return;
@@ -42,7 +47,7 @@ inline void emu_mbar_check_complete(uint64_t* bar)
     auto& fl = emu_inflight();
     for (size_t i = 0; i < fl.size();) {
         if (fl[i].bar == bar) {
-            std::memcpy(fl[i].dst, fl[i].src, fl[i].bytes);
+            emu_land_copy(fl[i].dst, fl[i].src, fl[i].bytes);
             fl[i] = fl.back();
             fl.pop_back();
         } else {
@@ -52,9 +57,10 @@ inline void emu_mbar_check_complete(uint64_t* bar)
     b->phase ^= 1;
     b->pending = b->expected;
     emu::S().progress = true;
+    EMU_HB_RELEASE(bar);  // the landed bytes and everything the arriving threads did before
 }
 
-inline void mbar_init(uint64_t* bar, int count)
+EMU_INTERNAL inline void mbar_init(uint64_t* bar, int count)
 {
     EmuMbar* b = emu_bar(bar);
     b->tx = 0;
@@ -63,33 +69,35 @@ inline void mbar_init(uint64_t* bar, int count)
     b->phase = 0;
 }
 inline void fence_mbar_init() {}
-inline void mbar_arrive(uint64_t* bar)
+EMU_INTERNAL inline void mbar_arrive(uint64_t* bar)
 {
     EmuMbar* b = emu_bar(bar);
     if (b->pending == 0) emu::die("mbarrier: more arrivals than expected");
+    EMU_HB_RELEASE(bar);
     b->pending -= 1;
     emu_mbar_check_complete(bar);
 }
-inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+EMU_INTERNAL inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     EmuMbar* b = emu_bar(bar);
     b->tx += (int64_t)bytes;
     mbar_arrive(bar);
 }
-inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) { return emu_bar(bar)->phase != (parity & 1u); }
-inline void mbar_wait(uint64_t* bar, uint32_t parity)
+EMU_INTERNAL inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) { return emu_bar(bar)->phase != (parity & 1u); }
+EMU_INTERNAL inline void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     emu::S().progress = true;
     while (!mbar_test_wait(bar, parity)) emu::yield();
+    EMU_HB_ACQUIRE(bar);
 }
 inline uint64_t l2_policy_evict_first() { return 0; }
 inline uint64_t l2_policy_evict_last() { return 0; }
 
-inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t)
+EMU_INTERNAL inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t)
 {
     if (((uintptr_t)dst_smem & 15) || ((uintptr_t)src_gmem & 15) || (bytes & 15) || bytes == 0)
         emu::die("cp.async.bulk: addresses must be 16-byte aligned and the size a non-zero multiple of 16");
-    std::memset(dst_smem, 0xCD, bytes);  // not visible before the barrier phase completes
+    emu_poison_copy(dst_smem, bytes);  // not visible before the barrier phase completes
     emu_inflight().push_back(EmuBulkCopy{dst_smem, src_gmem, bytes, bar});
     emu_bar(bar)->tx -= (int64_t)bytes;  // complete_tx
     emu_mbar_check_complete(bar);
@@ -99,19 +107,19 @@ inline void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
     if (((uintptr_t)src_gmem & 15) || (bytes & 15) || bytes == 0)
         emu::die("cp.async.bulk.prefetch: address must be 16-byte aligned and the size a non-zero multiple of 16");
 }
-inline void st_relaxed_sys_u64(uint64_t* p, uint64_t v) { *p = v; }
-inline void st_release_sys_u64(uint64_t* p, uint64_t v) { *p = v; }
-inline uint64_t ld_acquire_sys_u64(const uint64_t* p)
+inline void st_relaxed_sys_u64(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+inline void st_release_sys_u64(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+EMU_INTERNAL inline uint64_t ld_acquire_sys_u64(const uint64_t* p)
 {
     // a thread that reads the same address and gets the same value again is spinning: give the other
     // threads a turn without counting it as progress (so a flag nobody sets ends as a reported deadlock)
     static const uint64_t* last_addr[emu::kMaxThreads];
     static uint64_t last_val[emu::kMaxThreads];
     const int t = emu::S().cur;
-    const uint64_t v = *reinterpret_cast<const volatile uint64_t*>(p);
+    const uint64_t v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
     if (last_addr[t] == p && last_val[t] == v) {
         emu::yield();
-        return *reinterpret_cast<const volatile uint64_t*>(p);
+        return __atomic_load_n(p, __ATOMIC_ACQUIRE);
     }
     last_addr[t] = p;
     last_val[t] = v;

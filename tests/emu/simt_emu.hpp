@@ -29,6 +29,29 @@
 #undef __launch_bounds__
 #define __launch_bounds__(...)
 
+// EMU_TSAN: the same interpreter as a data-race detector.  Every CUDA thread is registered with
+// ThreadSanitizer as a fiber; barriers, warp collectives and mbarrier phases are annotated as
+// release/acquire pairs, atomics map to real atomics, and everything else -- every shared- or
+// global-memory access of the kernels -- is checked by TSan for a happens-before order.  A missing
+// __syncthreads / mbarrier wait is then reported as a race no matter which schedule ran.
+#ifdef EMU_TSAN
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+#define EMU_HB_RELEASE(p) __tsan_release((void*)(p))
+#define EMU_HB_ACQUIRE(p) __tsan_acquire((void*)(p))
+#define EMU_INTERNAL __attribute__((no_sanitize("thread")))  // the interpreter's own bookkeeping is not the subject
+#else
+#define EMU_HB_RELEASE(p) ((void)0)
+#define EMU_HB_ACQUIRE(p) ((void)0)
+#define EMU_INTERNAL
+#endif
+
 namespace emu {
 
 constexpr int kMaxThreads = 1024;
@@ -61,36 +84,49 @@ struct State {
     uint64_t collectives = 0, block_barriers = 0;  // statistics (per launch)
     int schedule = 0;                               // see run_block()
     uint64_t rng = 0x9E3779B97F4A7C15ull;
+    char block_token = 0;                           // happens-before edge between consecutive blocks / launches
+#ifdef EMU_TSAN
+    void* sched_fiber = nullptr;
+    void* fibers[kMaxThreads] = {};
+#endif
 };
-inline State& S()
+EMU_INTERNAL inline State& S()
 {
     static State* s = new State();
     return *s;
 }
 
-[[noreturn]] inline void die(const char* what)
+EMU_INTERNAL [[noreturn]] inline void die(const char* what)
 {
     State& s = S();
     std::fprintf(stderr, "simt_emu: %s (block %u, thread %d)\n", what, s.bidx.x, s.cur);
     std::abort();
 }
 
-inline void yield()
+EMU_INTERNAL inline void yield()
 {
     State& s = S();
+#ifdef EMU_TSAN
+    __tsan_switch_to_fiber(s.sched_fiber, 1);  // 1 = no_sync: a context switch is not a synchronisation
+#endif
     swapcontext(&s.lanes[s.cur].ctx, &s.sched);
 }
 
-inline void trampoline()
+EMU_INTERNAL inline void trampoline()
 {
     State& s = S();
+    EMU_HB_ACQUIRE(&s.block_token);  // blocks run one after another: ordered after the previous block and the host
     s.body();
+    EMU_HB_RELEASE(&s.block_token);
     s.lanes[s.cur].done = true;
     s.progress = true;
+#ifdef EMU_TSAN
+    __tsan_switch_to_fiber(s.sched_fiber, 1);  // 1 = no_sync: a context switch is not a synchronisation
+#endif
     // returning switches to uc_link == &s.sched
 }
 
-inline void run_block(int nthreads)
+EMU_INTERNAL inline void run_block(int nthreads)
 {
     State& s = S();
     if (nthreads > kMaxThreads) die("block too large");
@@ -106,7 +142,14 @@ inline void run_block(int nthreads)
         l.ctx.uc_link = &s.sched;
         makecontext(&l.ctx, trampoline, 0);
         l.done = false;
+#ifdef EMU_TSAN
+        if (!s.fibers[t]) s.fibers[t] = __tsan_create_fiber(0);
+#endif
     }
+#ifdef EMU_TSAN
+    s.sched_fiber = __tsan_get_current_fiber();
+#endif
+    EMU_HB_RELEASE(&s.block_token);  // what the host wrote before the launch is visible to the block
     // Resume order of the threads within a pass: 0 = ascending, 1 = descending, 2 = a fresh pseudo-random
     // permutation every pass (set_schedule()).  Results of a correctly synchronised kernel do not depend
     // on it; a read that is not ordered after its write by a barrier shows up as a difference.
@@ -127,6 +170,9 @@ inline void run_block(int nthreads)
             if (l.done) continue;
             s.cur = t;
             s.tidx = uint3{(unsigned)t, 0, 0};
+#ifdef EMU_TSAN
+            __tsan_switch_to_fiber(s.fibers[t], 1);
+#endif
             swapcontext(&s.sched, &l.ctx);
             if (l.done) --remaining;
         }
@@ -135,13 +181,14 @@ inline void run_block(int nthreads)
             die("deadlock: every live thread waits and nobody can make progress");
         }
     }
+    EMU_HB_ACQUIRE(&s.block_token);  // the host reads results after the block
 }
 
-inline void set_schedule(int mode) { S().schedule = mode; }
+EMU_INTERNAL inline void set_schedule(int mode) { S().schedule = mode; }
 
 // kernel<<<grid, block>>>(args...)  ==  emu::launch(grid, block, [&] { kernel(args...); })
 template <typename F>
-inline void launch(unsigned grid, unsigned block, F&& f)
+EMU_INTERNAL inline void launch(unsigned grid, unsigned block, F&& f)
 {
     State& s = S();
     s.gdim = dim3(grid, 1, 1);
@@ -154,7 +201,7 @@ inline void launch(unsigned grid, unsigned block, F&& f)
 }
 
 // ---- barriers ---------------------------------------------------------------------------------
-inline void block_barrier(int id, int expected)
+EMU_INTERNAL inline void block_barrier(int id, int expected)
 {
     State& s = S();
     if (id < 0 || id >= 16) die("bad barrier id");
@@ -162,33 +209,37 @@ inline void block_barrier(int id, int expected)
     const unsigned g = b.gen;
     s.progress = true;
     ++s.block_barriers;
+    EMU_HB_RELEASE(&b);
     if (++b.arrived == expected) {
         b.arrived = 0;
         ++b.gen;
     } else {
         while (b.gen == g) yield();
     }
+    EMU_HB_ACQUIRE(&b);
 }
-inline int warp_width()
+EMU_INTERNAL inline int warp_width()
 {
     State& s = S();
     const int base = (s.cur >> 5) << 5;
     return s.nthreads - base < 32 ? s.nthreads - base : 32;
 }
-inline void warp_barrier()
+EMU_INTERNAL inline void warp_barrier()
 {
     State& s = S();
     WarpState& w = s.warps[s.cur >> 5];
     const unsigned g = w.gen;
     s.progress = true;
+    EMU_HB_RELEASE(&w);
     if (++w.arrived == warp_width()) {
         w.arrived = 0;
         ++w.gen;
     } else {
         while (w.gen == g) yield();
     }
+    EMU_HB_ACQUIRE(&w);
 }
-inline void need_full(unsigned mask)
+EMU_INTERNAL inline void need_full(unsigned mask)
 {
     if (mask != 0xffffffffu) die("warp collective with a partial mask (not modelled)");
     if (warp_width() != 32) die("warp collective in a partial warp");
@@ -196,7 +247,7 @@ inline void need_full(unsigned mask)
 
 // every lane deposits a value, f(slots) is evaluated by every lane after all have arrived
 template <typename T, typename F>
-inline auto collective(unsigned mask, T v, F&& f)
+EMU_INTERNAL inline auto collective(unsigned mask, T v, F&& f)
 {
     static_assert(sizeof(T) <= 8, "collectives carry at most 8 bytes");
     need_full(mask);
@@ -315,16 +366,12 @@ EMU_REDUCE(__reduce_and_sync, unsigned, 0xffffffffu, acc& e)
 template <typename T>
 inline T atomicAdd(T* p, T v)
 {
-    T old = *p;
-    *p = old + v;
-    return old;
+    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 template <typename T>
 inline T atomicOr(T* p, T v)
 {
-    T old = *p;
-    *p = old | v;
-    return old;
+    return __atomic_fetch_or(p, v, __ATOMIC_RELAXED);
 }
 template <typename T>
 inline T atomicMax(T* p, T v)

@@ -403,3 +403,30 @@ def test_emu_address_sanitizer():
     r = subprocess.run([sys.executable, os.path.join(EMU, "asan_check.py"), lib], capture_output=True, text=True,
                        env=env, timeout=900)
     assert r.returncode == 0 and "asan check complete" in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+
+
+def test_emu_thread_sanitizer():
+    """Data-race check of the kernels' shared-memory protocol.  tests/emu/tsan_check.cpp builds the
+    interpreter with -fsanitize=thread -DEMU_TSAN: every CUDA thread is a TSan fiber, __syncthreads /
+    named barriers / warp collectives / mbarrier phases are the only release-acquire edges, atomics are
+    atomics, the bytes a bulk copy lands are ordinary writes.  Any access of the shipped kernel,
+    variant 3, the fused launch or the carry exchange that is not ordered by those edges is reported
+    (removing the barrier after the row-end scatter, or the mbarrier wait, gives dozens of reports)."""
+    import shutil
+
+    gxx = shutil.which("g++")
+    libtsan = subprocess.run([gxx, "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(libtsan):
+        pytest.skip("libtsan not available")
+    out_dir = os.path.join(EMU, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "tsan_check")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fno-strict-aliasing", "-ffp-contract=off", "-w",
+                    "-fsanitize=thread", "-DEMU_TSAN", "-I", EMU, "-I", CSRC, "-I", "/usr/local/cuda/include",
+                    os.path.join(EMU, "tsan_check.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
+    if "unexpected memory mapping" in r.stderr or "FATAL: ThreadSanitizer" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot start in this environment: " + r.stderr[-200:])
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+    assert r.returncode == 0 and "tsan check complete" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
