@@ -398,7 +398,8 @@ def test_emu_address_sanitizer():
     libasan = subprocess.run([gxx, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(libasan) or not os.path.exists(libasan):
         pytest.skip("libasan.so not available")
-    lib = build("asan", extra=["-fsanitize=address", "-fno-omit-frame-pointer"])
+    lib = build("asan", extra=["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                               "-fno-omit-frame-pointer"])  # undefined behaviour (shifts, overflow, alignment) aborts too
     env = dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     r = subprocess.run([sys.executable, os.path.join(EMU, "asan_check.py"), lib], capture_output=True, text=True,
                        env=env, timeout=900)
