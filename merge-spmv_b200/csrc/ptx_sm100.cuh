@@ -50,10 +50,25 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Experiment (off = 0): give try_wait a suspend-time hint in nanoseconds, so that a waiting warp stays
+// parked in hardware instead of re-issuing the poll (the poll loop is ~11 % of the tile kernel's
+// executed instructions, which matters where the kernel is issue-bound).
+#ifndef MSPMV_MBAR_SUSPEND_NS
+#define MSPMV_MBAR_SUSPEND_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
     do {
+#if MSPMV_MBAR_SUSPEND_NS > 0
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MSPMV_MBAR_SUSPEND_NS)
+            : "memory");
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -61,6 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+#endif
     } while (!ok);
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first()

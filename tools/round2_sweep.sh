@@ -51,6 +51,10 @@ for W in uniform_1m_64 powerlaw_2m banded_10m uniform_1m_64_local; do
         run "shipped kernel, $I" MSPMV_LIB=$V/libmergespmv_$I.so -- --workload $W
         run "tile_variant=3, $I" MSPMV_LIB=$V/libmergespmv_$I.so -- --workload $W --option tile_variant=3
     done
+    for M in mbar2us mbar20us; do
+        run "shipped kernel, try_wait hint $M" MSPMV_LIB=$V/libmergespmv_$M.so -- --workload $W
+        run "tile_variant=3, try_wait hint $M" MSPMV_LIB=$V/libmergespmv_$M.so -- --workload $W --option tile_variant=3
+    done
     run "tile_variant=3, popcount prefix" MSPMV_LIB=$V/libmergespmv_v3popc.so -- --workload $W --option tile_variant=3
     run "tile_variant=3, shuffle-flag scan" MSPMV_LIB=$V/libmergespmv_v3shflscan.so -- --workload $W --option tile_variant=3
     run "tile_variant=3, 48 registers"  MSPMV_LIB=$V/libmergespmv_v3regs48.so -- --workload $W --option tile_variant=3
