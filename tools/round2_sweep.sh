@@ -2,7 +2,7 @@
 # First GPU call of the next round: parity of the opt-in variants, then one timing table of every
 # variant on the four single-GPU workloads.  Everything lands in gpurun_out/ (merged back by gpurun).
 #
-#   gpurun --timeout 2700 -- 'bash tools/round2_sweep.sh'     (about 60 bench.py runs of ~25 s each)
+#   gpurun --timeout 1800 -- 'bash tools/round2_sweep.sh'     (~15 min; FULL=1 adds the secondary switches, ~10 min more)
 #
 # Variants (all off by default; kernel logic already covered on CPU by tests/test_kernel_emu.py):
 #   tile_variant=3          thread-blocked gathers, products in registers (csrc/spmv_tile3.cuh)
@@ -42,39 +42,28 @@ PYEOF
 
 make -C merge-spmv_b200 -s -j4 variants 2>&1 | tail -3
 V=merge-spmv_b200/variants
-echo "== timing: ms per CsrMV step (CUDA-graph replay, $STEPS steps)" | tee -a "$OUT/sweep_r02.txt"
-for W in uniform_1m_64 powerlaw_2m banded_10m uniform_1m_64_local; do
-    run "shipped"                 -- --workload $W
-    run "tile_variant=3"          -- --workload $W --option tile_variant=3
-    run "tile_variant=3 carve 56" MSPMV_TILE_CARVEOUT=56 -- --workload $W --option tile_variant=3
-    for I in ipt7_11 ipt8_12 ipt10_14 ipt11_15; do
-        run "shipped kernel, $I" MSPMV_LIB=$V/libmergespmv_$I.so -- --workload $W
-        run "tile_variant=3, $I" MSPMV_LIB=$V/libmergespmv_$I.so -- --workload $W --option tile_variant=3
-    done
-    for M in mbar2us mbar20us; do
-        run "shipped kernel, try_wait hint $M" MSPMV_LIB=$V/libmergespmv_$M.so -- --workload $W
-        run "tile_variant=3, try_wait hint $M" MSPMV_LIB=$V/libmergespmv_$M.so -- --workload $W --option tile_variant=3
-    done
-    run "tile_variant=3, popcount prefix" MSPMV_LIB=$V/libmergespmv_v3popc.so -- --workload $W --option tile_variant=3
-    run "tile_variant=3, shuffle-flag scan" MSPMV_LIB=$V/libmergespmv_v3shflscan.so -- --workload $W --option tile_variant=3
-    run "tile_variant=3, 48 registers"  MSPMV_LIB=$V/libmergespmv_v3regs48.so -- --workload $W --option tile_variant=3
-done
+echo "== timing: ms per CsrMV step (CUDA-graph replay, $STEPS steps; one process per build, both kernels in it)" | tee -a "$OUT/sweep_r02.txt"
+lib() {  # label, env assignments... : times tile_variant 2 and 3 of one build on the four workloads
+    local label=$1; shift
+    env "$@" timeout 900 $PY tools/sweep_lib.py --label "$label" --steps "$STEPS" ${WL:+--workloads "$WL"} > "$OUT/sweep_lib.log" 2>&1
+    if grep -qE "ms \|" "$OUT/sweep_lib.log"; then grep -E "^#|\|" "$OUT/sweep_lib.log" | tee -a "$OUT/sweep_r02.txt"
+    else echo "$label FAILED:" | tee -a "$OUT/sweep_r02.txt"; tail -8 "$OUT/sweep_lib.log" | tee -a "$OUT/sweep_r02.txt"; fi
+}
+lib shipped-build
+for B in ipt8_12 mbar2us; do lib $B MSPMV_LIB=$V/libmergespmv_$B.so; done
+if [ "${FULL:-0}" = 1 ]; then
+    for B in ipt7_11 ipt10_14 ipt11_15 mbar20us v3popc v3shflscan v3regs48; do lib $B MSPMV_LIB=$V/libmergespmv_$B.so; done
+fi
 echo "== shared-memory carve-out (L1 left for gather misses in flight) on the random-column workloads" | tee -a "$OUT/sweep_r02.txt"
-for W in uniform_1m_64 powerlaw_2m; do
-    for C in 50 56 62 85; do
-        run "shipped, carve-out $C %"        MSPMV_TILE_CARVEOUT=$C -- --workload $W
-        run "tile_variant=3, carve-out $C %" MSPMV_TILE_CARVEOUT=$C -- --workload $W --option tile_variant=3
-    done
+# 7 / 11 items per thread are ~14 KB per block: 8-9 blocks fit a 132 KB shared-memory configuration (the gather
+# ceiling is 275 G/s there, 252 at 164 KB, 127 at 196 KB: profiles/microbench_r01.txt)
+WL=uniform_1m_64,powerlaw_2m
+for C in 50 56 62; do
+    lib "carve-out $C %" MSPMV_TILE_CARVEOUT=$C
+    lib "ipt7_11, carve-out $C %" MSPMV_LIB=$V/libmergespmv_ipt7_11.so MSPMV_TILE_CARVEOUT=$C
 done
-# smaller tiles leave more of the 228 KB to L1: 7 / 11 items per thread are ~13 KB per block, so 9 blocks fit
-# a 132 KB shared-memory configuration (the gather ceiling is 275 G/s there, 252 at 164 KB, 127 at 196 KB:
-# profiles/microbench_r01.txt)
-for W in uniform_1m_64 powerlaw_2m; do
-    for C in 50 56 62; do
-        run "shipped, ipt7_11, carve-out $C %"        MSPMV_LIB=$V/libmergespmv_ipt7_11.so MSPMV_TILE_CARVEOUT=$C -- --workload $W
-        run "tile_variant=3, ipt7_11, carve-out $C %" MSPMV_LIB=$V/libmergespmv_ipt7_11.so MSPMV_TILE_CARVEOUT=$C -- --workload $W --option tile_variant=3
-    done
-done
+[ "${FULL:-0}" = 1 ] && lib "carve-out 85 %" MSPMV_TILE_CARVEOUT=85
+unset WL
 echo "== small matrices (config 1 shape): launch-latency-bound" | tee -a "$OUT/sweep_r02.txt"
 run "shipped (3 launches)"        -- --workload cpu_uniform_16k --steps 2000
 run "small_fused_tiles=4096"      -- --workload cpu_uniform_16k --steps 2000 --option small_fused_tiles=4096
