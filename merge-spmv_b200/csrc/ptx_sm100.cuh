@@ -14,6 +14,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// the block's dynamic shared memory (one spelling for nvcc, another for the CPU interpreter)
+#define MSPMV_DYNAMIC_SHARED(name) extern __shared__ unsigned char name[]
+
 namespace mspmv {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)

@@ -118,7 +118,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     constexpr int NRW = C::REDUCERS / 32;   // reduce warps: 0 .. NRW-1
     constexpr int NGW = C::GATHERERS / 32;  // gather warps: NRW .. NRW+NGW-1; producer: NRW+NGW
     constexpr int IPT = C::IPT;
-    extern __shared__ unsigned char smem_raw[];
+    MSPMV_DYNAMIC_SHARED(smem_raw);
     StreamSmem<T>& sm =
         *reinterpret_cast<StreamSmem<T>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
 
@@ -395,6 +395,7 @@ __global__ __launch_bounds__(StreamCfg<T>::THREADS, StreamCfg<T>::CTAS_PER_SM) v
     }
 }
 
+#ifndef MSPMV_PTX_HEADER  // host-side launch: not part of what the CPU interpreter of tests/emu compiles
 template <typename T, bool AXPBY>
 static int stream_launch(const StreamGeom& g, const T* values, const int* row_offsets, const int* col,
                          const T* x, T* y, int num_rows, int num_nonzeros, int2* swath_coords,
@@ -420,5 +421,6 @@ static int stream_launch(const StreamGeom& g, const T* values, const int* row_of
                                                               shift_v, shift_c, shift_r);
     return 0;
 }
+#endif  // MSPMV_PTX_HEADER
 
 }  // namespace mspmv

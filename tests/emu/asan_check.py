@@ -21,12 +21,23 @@ for sfx, fp in (("f64", C.c_double), ("f32", C.c_float)):
     f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p, C.c_int]
 
 
+for sfx, fp in (("f64", C.c_double), ("f32", C.c_float)):
+    f = getattr(lib, "emu_csrmv_stream_" + sfx)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p]
+
+
 def strict(ro, col, val, x, mode):
     ro, col = np.array(ro, np.int32, copy=True), np.array(col, np.int32, copy=True)
     val, x = np.array(val, copy=True), np.array(x, copy=True)
     rows, nnz = ro.size - 1, int(ro[-1])
     y = np.full(rows, np.nan, val.dtype)
     stats = np.zeros(4, np.int32)
+    if mode >= 10:  # the stream engine on a pretend device of mode - 10 SMs
+        fn = lib.emu_csrmv_stream_f64 if val.dtype == np.float64 else lib.emu_csrmv_stream_f32
+        assert fn(val.ctypes.data, ro.ctypes.data, col.ctypes.data, x.ctypes.data, y.ctypes.data, rows, nnz, 1.0, 0.0,
+                  0, mode - 10, stats.ctypes.data) == 0
+        return y
     fn = lib.emu_csrmv_f64 if val.dtype == np.float64 else lib.emu_csrmv_f32
     assert fn(val.ctypes.data, ro.ctypes.data, col.ctypes.data, x.ctypes.data, y.ctypes.data, rows, nnz, 1.0, 0.0,
               0, 0, stats.ctypes.data, mode) == 0
@@ -90,7 +101,7 @@ for rows, cols, mean_len, empty, longs in shapes:
     ro, col = random_csr(rng, rows, cols, mean_len, empty, longs)
     nnz = int(ro[-1])
     for dt in (np.float64, np.float32):
-        for mode in (0, 1, 3):  # shipped three-launch path, fused single launch, tile variant 3
+        for mode in (0, 1, 3, 11, 13):  # three-launch path, fused single launch, tile variant 3, stream engine (1 / 3 SMs)
             y = strict(ro, col, np.ones(nnz, dt), np.ones(cols, dt), mode)
             assert np.array_equal(y, np.diff(ro).astype(dt)), (rows, cols, mode)
 for rows, cols, mean_len, empty, longs in [(700, 900, 7, 0.2, 1), (5, 7, 2, 0.0, 0), (1, 9, 5, 0.0, 0), (2500, 40, 1, 0.4, 0)]:

@@ -11,6 +11,9 @@
 
 #include "simt_emu.hpp"
 
+// dynamic shared memory: one static buffer of the largest size a block can ask for
+#define MSPMV_DYNAMIC_SHARED(name) alignas(1024) static unsigned char name[232448]
+
 namespace mspmv {
 
 struct EmuMbar {  // lives in the kernel's 8-byte mbarrier word
@@ -125,6 +128,16 @@ EMU_INTERNAL inline uint64_t ld_acquire_sys_u64(const uint64_t* p)
     last_val[t] = v;
     return v;
 }
+// cp.async (LDGSTS): the copy is performed at issue; the thread's arrival on the barrier (which the
+// hardware defers until its copies have landed) follows it in program order
+template <int BYTES>
+inline void cp_async_gather(void* dst_smem, const void* src_gmem)
+{
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async copies 4, 8 or 16 bytes");
+    if (((uintptr_t)dst_smem | (uintptr_t)src_gmem) & (BYTES - 1)) emu::die("cp.async: misaligned address");
+    std::memcpy(dst_smem, src_gmem, BYTES);
+}
+inline void cp_async_arrive_noinc(uint64_t* bar) { mbar_arrive(bar); }
 inline void fence_proxy_async() {}
 inline void named_bar_sync(int id, int threads) { emu::block_barrier(id, threads); }
 

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>  // vector types; __device__ / __global__ expand to nothing for a host compiler
 #include <ucontext.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -413,3 +414,6 @@ inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 inline long long min(long long a, long long b) { return a < b ? a : b; }
 inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline long min(long a, long b) { return a < b ? a : b; }  // int64_t is long on LP64
+inline long max(long a, long b) { return a > b ? a : b; }
+using std::fma;  // <cmath>: float and double overloads

@@ -8,6 +8,7 @@
 #include "spmv_tile.cuh"
 #include "spmv_tile3.cuh"
 #include "carry_exchange.cuh"
+#include "spmv_stream.cuh"
 
 #include <vector>
 
@@ -84,9 +85,60 @@ int run(const T* values, const int* row_offsets, const int* col, const T* x, T* 
     return 0;
 }
 
+// the alternative "stream" engine (persistent swaths, three warp-specialised stages over mbarrier rings):
+// stream_launch() + the runs fix-up of csrmv_launch(), with `sm_count` standing in for the device's SM count
+template <typename T, bool AXPBY>
+int run_stream(const T* values, const int* row_offsets, const int* col, const T* x, T* y, int num_rows,
+               int num_nonzeros, T alpha, T beta, int sm_count, int* stats)
+{
+    if (num_rows <= 0) return 0;
+    const StreamGeom g = stream_geometry<T>((int64_t)num_rows + num_nonzeros, sm_count);
+    const int n = g.num_swaths;
+    std::vector<int2> coords((size_t)n + 1);
+    std::vector<int> carry_rows((size_t)n);
+    std::vector<T> carry_vals((size_t)n);
+    std::memset(coords.data(), 0xEE, coords.size() * sizeof(int2));
+    std::memset(carry_rows.data(), 0xEE, carry_rows.size() * sizeof(int));
+    std::memset(carry_vals.data(), 0xEE, carry_vals.size() * sizeof(T));
+    const int sv = shift_of<T>(values), sc = shift_of<int>(col), sr = shift_of<int>(row_offsets);
+    const bool vec = sv == 0 && sc == 0;
+    emu::launch((unsigned)n, (unsigned)g.threads, [&] {
+        if (vec)
+            spmv_stream_kernel<T, AXPBY, true>(values, row_offsets, col, x, y, num_rows, num_nonzeros, g.swath_items,
+                                               coords.data(), carry_rows.data(), carry_vals.data(), alpha, beta, sv, sc, sr);
+        else
+            spmv_stream_kernel<T, AXPBY, false>(values, row_offsets, col, x, y, num_rows, num_nonzeros, g.swath_items,
+                                                coords.data(), carry_rows.data(), carry_vals.data(), alpha, beta, sv, sc, sr);
+    });
+    if (n > 1)
+        emu::launch((unsigned)((n + 255) / 256), 256, [&] {
+            carry_fixup_runs_kernel<T, AXPBY>(carry_rows.data(), carry_vals.data(), n, num_rows, y, alpha);
+        });
+    if (stats) {
+        stats[0] = n;
+        stats[1] = g.tile_items;
+        stats[2] = g.threads;
+        stats[3] = g.swath_items;
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int emu_csrmv_stream_f64(const double* v, const int* ro, const int* ci, const double* x, double* y, int rows, int nnz,
+                         double alpha, double beta, int axpby, int sm_count, int* stats)
+{
+    return axpby ? run_stream<double, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, sm_count, stats)
+                 : run_stream<double, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, sm_count, stats);
+}
+int emu_csrmv_stream_f32(const float* v, const int* ro, const int* ci, const float* x, float* y, int rows, int nnz,
+                         float alpha, float beta, int axpby, int sm_count, int* stats)
+{
+    return axpby ? run_stream<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, sm_count, stats)
+                 : run_stream<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, sm_count, stats);
+}
 
 // mode: 0 = search + tile + fix-up (shipped), 1 = single fused launch, 3 = search + tile variant 3 + fix-up
 int emu_csrmv_f64(const double* v, const int* ro, const int* ci, const double* x, double* y, int rows, int nnz,

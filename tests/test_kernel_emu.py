@@ -41,7 +41,7 @@ def build(name, extra=()):
     out = os.path.join(out_dir, f"libtile_emu_{name}.so")
     srcs = [os.path.join(EMU, f) for f in ("tile_emu.cpp", "simt_emu.hpp", "ptx_emu.cuh")]
     srcs += [os.path.join(CSRC, f) for f in ("spmv_tile.cuh", "spmv_tile3.cuh", "merge_common.cuh", "tma_stage.cuh",
-                                             "ptx_sm100.cuh", "carry_exchange.cuh")]
+                                             "ptx_sm100.cuh", "carry_exchange.cuh", "spmv_stream.cuh")]
     if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(s) for s in srcs + [__file__]):
         return out
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fno-strict-aliasing", "-fno-gnu-unique", "-ffp-contract=off", "-fPIC", "-shared", "-w",
@@ -58,10 +58,13 @@ class Emu:
             f = getattr(self.lib, "emu_csrmv_" + sfx)
             f.restype = C.c_int
             f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p, C.c_int]
+            g = getattr(self.lib, "emu_csrmv_stream_" + sfx)
+            g.restype = C.c_int
+            g.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p]
         self.lib.emu_merge_path_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
 
     def csrmv(self, ro, col, val, x, y_in=None, alpha=1.0, beta=0.0, axpby=False, misalign=(0, 0, 0),
-              prefetch_ahead=0, fused=False, variant=2):
+              prefetch_ahead=0, fused=False, variant=2, stream_sms=0):
         """misalign = element offsets (values, col, row_offsets) of the array bases from 16 bytes."""
         dt = val.dtype
         rows, nnz = ro.size - 1, int(ro[-1])
@@ -86,8 +89,13 @@ class Emu:
         stats = np.zeros(4, np.int32)
         fn = getattr(self.lib, "emu_csrmv_" + ("f64" if dt == np.float64 else "f32"))
         mode = 1 if fused else (3 if variant == 3 else 0)
-        rc = fn(v.ctypes.data, r.ctypes.data, c.ctypes.data, xx.ctypes.data, y.ctypes.data, rows, nnz,
-                alpha, beta, int(axpby), prefetch_ahead, stats.ctypes.data, mode)
+        if stream_sms:  # the alternative "stream" engine on a pretend device with that many SMs
+            fn = getattr(self.lib, "emu_csrmv_stream_" + ("f64" if dt == np.float64 else "f32"))
+            rc = fn(v.ctypes.data, r.ctypes.data, c.ctypes.data, xx.ctypes.data, y.ctypes.data, rows, nnz,
+                    alpha, beta, int(axpby), stream_sms, stats.ctypes.data)
+        else:
+            rc = fn(v.ctypes.data, r.ctypes.data, c.ctypes.data, xx.ctypes.data, y.ctypes.data, rows, nnz,
+                    alpha, beta, int(axpby), prefetch_ahead, stats.ctypes.data, mode)
         assert rc == 0
         self.stats = stats
         return y
@@ -431,3 +439,30 @@ def test_emu_thread_sanitizer():
         pytest.skip("ThreadSanitizer cannot start in this environment: " + r.stderr[-200:])
     assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:4000]
     assert r.returncode == 0 and "tsan check complete" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_emu_stream_engine(emu0, orc, dt):
+    """The alternative "stream" engine (MSPMV_ENGINE=stream: persistent swaths, TMA producer warps ->
+    cp.async gather warps -> reduce warps over mbarrier rings) under the interpreter, on pretend
+    devices of 1 and 3 SMs, aligned (vectorised gather stage) and misaligned bases, alpha/beta."""
+    rng = np.random.default_rng(88)
+    for rows, cols, mean_len, empty, longs in SHAPES:
+        ro, col = random_csr(rng, rows, cols, mean_len, empty, longs)
+        nnz = int(ro[-1])
+        for sms, mis in ((1, (0, 0, 0)), (3, (0, 0, 0)), (2, (1, 2, 3))):
+            y = emu0.csrmv(ro, col, np.ones(nnz, dt), np.ones(cols, dt), stream_sms=sms, misalign=mis)
+            assert np.array_equal(y, np.diff(ro).astype(dt)), (rows, cols, sms, mis, "exact")
+        val = (0.5 + rng.random(nnz)).astype(dt)
+        x = (0.5 + rng.random(cols)).astype(dt)
+        got = emu0.csrmv(ro, col, val, x, stream_sms=3)
+        assert_close(got, orc.merge_csrmv(ro, col, val, x, num_threads=8), ro, dt, f"{rows}x{cols}")
+    ro, col = random_csr(rng, 900, 400, 5, 0.2, 1)
+    nnz = int(ro[-1])
+    val = (0.5 + rng.random(nnz)).astype(dt)
+    x = (0.5 + rng.random(400)).astype(dt)
+    y0 = rng.random(900).astype(dt)
+    ax = orc.merge_csrmv(ro, col, val, x, num_threads=4)
+    got = emu0.csrmv(ro, col, val, x, y_in=y0, alpha=-0.75, beta=0.5, axpby=True, stream_sms=2)
+    want = (dt(-0.75) * ax + dt(0.5) * y0).astype(dt)
+    assert np.all(np.abs(got - want) <= (1e-10 if dt == np.float64 else 3e-6) * (np.abs(0.75 * ax) + np.abs(0.5 * y0)))
