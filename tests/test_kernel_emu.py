@@ -320,8 +320,8 @@ def test_emu_nvlink_carry_exchange(emu0, world, use_f32):
 @pytest.mark.parametrize("schedule", [0, 1, 2])
 def test_emu_fuzz_small_matrices(emu0, orc, schedule):
     """400 random small matrices (empty rows, single long rows, constant rows, sparse patterns),
-    random base-pointer misalignment, both value types; shipped kernel, variant 3 and the fused
-    single-launch path.  Small-integer inputs make the result exact in any summation order, so the
+    random base-pointer misalignment, both value types; shipped kernel, variant 3, the fused
+    single-launch path and the stream engine.  Small-integer inputs make the result exact in any summation order, so the
     comparison with SpmvGold (cpu_spmv.cpp:257-277) is bit for bit."""
     # schedule: order in which the interpreter resumes the threads of a block (ascending, descending,
     # random per pass) -- a kernel whose shared-memory reads are properly ordered after the writes by
@@ -359,8 +359,9 @@ def test_emu_fuzz_small_matrices(emu0, orc, schedule):
         mis = (int(rng.integers(per16)), int(rng.integers(4)), int(rng.integers(4)))
         variant = 3 if rng.random() < 0.4 else 2
         fused = variant == 2 and rng.random() < 0.3
-        got = emu0.csrmv(ro, col, val, x, misalign=mis, variant=variant, fused=fused)
-        assert np.array_equal(got, want), (it, rows, cols, nnz, mode, mis, variant, fused, schedule)
+        stream_sms = int(rng.integers(1, 5)) if rng.random() < 0.15 else 0  # now and then the stream engine instead
+        got = emu0.csrmv(ro, col, val, x, misalign=mis, variant=variant, fused=fused, stream_sms=stream_sms)
+        assert np.array_equal(got, want), (it, rows, cols, nnz, mode, mis, variant, fused, stream_sms, schedule)
     emu0.lib.emu_set_schedule(0)
 
 
