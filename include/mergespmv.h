@@ -197,7 +197,9 @@ int mspmv_set_engine(const char* name);
  *                        0: off (default).  -1: back to the MSPMV_SMALL_FUSED environment value.
  *   "tile_variant"       2: the shipped tile kernel (default).  3: spmv_tile3_kernel -- thread-blocked
  *                        gathers, products kept in registers (csrc/spmv_tile3.cuh); same bits.
- *                        -1: back to the MSPMV_TILE_VARIANT environment value. */
+ *                        0: chosen per call -- variant 3 when (rows + nnz) / rows is at most
+ *                        "auto_v3_max_row_items" (default 0: never).  -1: back to MSPMV_TILE_VARIANT.
+ *   "auto_v3_max_row_items"  the threshold of tile_variant 0. */
 int mspmv_set_option(const char* name, int value);
 
 #ifdef __cplusplus

@@ -92,18 +92,26 @@ static int small_fused_tiles()
     return env > 0 ? env : 0;
 }
 
-// Tile kernel variant: 2 = tile_body (shipped), 3 = tile_body_v3 (spmv_tile3.cuh; opt-in until timed).
-// MSPMV_TILE_VARIANT=3 or mspmv_set_option("tile_variant", 3).
+// Tile kernel variant: 2 = tile_body (shipped), 3 = tile_body_v3 (spmv_tile3.cuh; opt-in until timed),
+// 0 = per call by average row length: variant 3 when (rows + nnz) / rows <= "auto_v3_max_row_items"
+// (short rows are where the tile kernel is instruction-bound; the threshold is 0 = never until the
+// round-2 sweep has placed it).  MSPMV_TILE_VARIANT / mspmv_set_option("tile_variant", v).
 static std::atomic<int> g_tile_variant{-1};
-static int tile_variant()
+static std::atomic<int> g_auto_v3_max_row_items{0};
+static int tile_variant(int num_rows, int num_nonzeros)
 {
     int v = g_tile_variant.load(std::memory_order_relaxed);
-    if (v >= 0) return v;
-    static int env = [] {
-        const char* e = std::getenv("MSPMV_TILE_VARIANT");
-        return e ? std::atoi(e) : 2;
-    }();
-    return env == 3 ? 3 : 2;
+    if (v < 0) {
+        static int env = [] {
+            const char* e = std::getenv("MSPMV_TILE_VARIANT");
+            return e ? std::atoi(e) : 2;
+        }();
+        v = (env == 3 || env == 0) ? env : 2;
+    }
+    if (v != 0) return v;
+    const int limit = g_auto_v3_max_row_items.load(std::memory_order_relaxed);
+    const int64_t items = (int64_t)num_rows + num_nonzeros;
+    return (num_rows > 0 && items <= (int64_t)limit * num_rows) ? 3 : 2;
 }
 
 static inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
@@ -249,7 +257,7 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
             configured[dev & 63].store(true, std::memory_order_relaxed);
         }
     }
-    if (tile_variant() == 3) {
+    if (tile_variant(num_rows, num_nonzeros) == 3) {
         static std::atomic<bool> v3_configured[64];  // per device; a benign race only repeats the call
         int dev = 0;
         cudaGetDevice(&dev);
@@ -711,8 +719,12 @@ int mspmv_set_option(const char* name, int value)
         return 0;
     }
     if (!std::strcmp(name, "tile_variant")) {
-        if (value != -1 && value != 2 && value != 3) return 1;
+        if (value != -1 && value != 0 && value != 2 && value != 3) return 1;
         g_tile_variant = value;  // -1: back to the environment / default
+        return 0;
+    }
+    if (!std::strcmp(name, "auto_v3_max_row_items")) {
+        g_auto_v3_max_row_items = value < 0 ? 0 : value;
         return 0;
     }
     return 1;
