@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,7 @@
 #include "spmv_stream.cuh"
 #include "spmv_tile.cuh"
 #include "spmv_tile3.cuh"
+#include "spmv_pipe.cuh"
 #include "carry_exchange.cuh"
 
 namespace mspmv {
@@ -56,7 +58,7 @@ static int device_info(DeviceInfo& out)
     return 0;
 }
 
-enum class Engine { Auto, Tile, Stream };
+enum class Engine { Auto, Tile, Stream, Pipe };
 
 static std::atomic<int> g_engine_override{-1};
 
@@ -68,6 +70,7 @@ static Engine engine_from_env()
         const char* s = std::getenv("MSPMV_ENGINE");
         if (s && !std::strcmp(s, "tile")) return Engine::Tile;
         if (s && !std::strcmp(s, "stream")) return Engine::Stream;
+        if (s && !std::strcmp(s, "pipe")) return Engine::Pipe;
         return Engine::Auto;
     }();
     return e;
@@ -114,6 +117,51 @@ static int tile_variant(int num_rows, int num_nonzeros)
     return (num_rows > 0 && items <= (int64_t)limit * num_rows) ? 3 : 2;
 }
 
+// ---- pipe engine knobs (mspmv_set_option / environment; -1 = environment / default) ----------------
+//   pipe_search        1: the producer warp finds the tile coordinates itself (one launch per CsrMV, default)
+//                      0: tile_search_kernel first (two launches)
+//   pipe_blocks_per_sm resident blocks per SM the grid is sized for (0 = as many as the shared-memory budget allows)
+//   pipe_smem_kb       shared-memory budget per SM in KB (the rest of the 228 KB stays L1 for the gather misses)
+static std::atomic<int> g_pipe_search{-1}, g_pipe_blocks_per_sm{-1}, g_pipe_smem_kb{-1};
+static int env_int(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+static int pipe_search()
+{
+    int v = g_pipe_search.load(std::memory_order_relaxed);
+    if (v >= 0) return v;
+    static int env = env_int("MSPMV_PIPE_SEARCH", 1);
+    return env;
+}
+static int pipe_blocks_per_sm_opt()
+{
+    int v = g_pipe_blocks_per_sm.load(std::memory_order_relaxed);
+    if (v >= 0) return v;
+    static int env = env_int("MSPMV_PIPE_BLOCKS_PER_SM", 0);
+    return env;
+}
+static int pipe_smem_kb()
+{
+    int v = g_pipe_smem_kb.load(std::memory_order_relaxed);
+    if (v > 0) return v;
+    static int env = env_int("MSPMV_PIPE_SMEM_KB", 160);
+    return env;
+}
+
+template <typename T>
+static int pipe_blocks_per_sm()
+{
+    const int per_block = (int)pipe_smem_bytes<T>() + 1024;  // + the per-block reservation of the driver
+    int b = pipe_smem_kb() * 1024 / per_block;
+    const int by_threads = 2048 / PipeCfg<T>::THREADS;
+    if (b > by_threads) b = by_threads;
+    const int want = pipe_blocks_per_sm_opt();
+    if (want > 0 && want < b) b = want;
+    return b < 1 ? 1 : b;
+}
+
 static inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 
 template <typename T>
@@ -122,6 +170,7 @@ struct Plan {
     int64_t merge_items;
     int num_tiles;      // tile engine: tiles; stream engine: swaths (threadblocks)
     int num_fix_blocks;  // tile engine: level-1 fix-up blocks
+    int num_blocks;      // pipe engine: threadblocks (each owns a contiguous run of tiles)
     size_t off_coords, off_carry_rows, off_carry_vals, off_carry2_rows, off_carry2_vals, off_ticket, bytes;
     StreamGeom geom;    // stream engine only
 };
@@ -134,9 +183,14 @@ static int make_plan(int num_rows, int num_nonzeros, Plan<T>& p)
     DeviceInfo di;
     int rc = device_info(di);
     if (rc) return rc;
-    if (e == Engine::Auto) e = Engine::Tile;
+    if (e == Engine::Auto) e = Engine::Pipe;
     p.engine = e;
-    if (e == Engine::Stream) {
+    p.num_blocks = 0;
+    if (e == Engine::Pipe) {
+        p.num_tiles = (int)((p.merge_items + PipeCfg<T>::TILE - 1) / PipeCfg<T>::TILE);
+        const int resident = di.sm_count * pipe_blocks_per_sm<T>();
+        p.num_blocks = p.num_tiles < resident ? p.num_tiles : resident;
+    } else if (e == Engine::Stream) {
         p.geom = stream_geometry<T>(p.merge_items, di.sm_count);
         p.num_tiles = p.geom.num_swaths;
     } else {
@@ -146,6 +200,7 @@ static int make_plan(int num_rows, int num_nonzeros, Plan<T>& p)
     p.off_coords = off;
     off += align256(sizeof(int2) * (size_t)(p.num_tiles + 1));
     p.off_carry_rows = off;
+    // (the pipe engine writes one carry per block, but its grid depends on run-time options: size for tiles)
     off += align256(sizeof(int) * (size_t)p.num_tiles);
     p.off_carry_vals = off;
     off += align256(sizeof(T) * (size_t)p.num_tiles);
@@ -186,6 +241,45 @@ static int tile_prefetch_ahead()
     return di.sm_count * 11;
 }
 
+template <typename T, bool AXPBY, bool SEARCH>
+static int pipe_launch_impl(const Plan<T>& p, int2* coords, int2* coords_out, int* carry_rows, T* carry_vals,
+                            unsigned int* ticket, const T* values, const int* row_offsets, const int* col,
+                            const T* x, T* y, int num_rows, int num_nonzeros, T alpha, T beta,
+                            cudaStream_t stream, int debug_sync)
+{
+    using C = PipeCfg<T>;
+    constexpr size_t smem = pipe_smem_bytes<T>();
+    static std::atomic<bool> configured[64];  // per device; a benign race only repeats the calls
+    int dev = 0;
+    MSPMV_TRY(cudaGetDevice(&dev));
+    if (!configured[dev & 63].load(std::memory_order_relaxed)) {
+        MSPMV_TRY(cudaFuncSetAttribute(spmv_pipe_kernel<T, AXPBY, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        int pct = (pipe_smem_kb() * 100 + 227) / 228;
+        if (pct > 100) pct = 100;
+        MSPMV_TRY(cudaFuncSetAttribute(spmv_pipe_kernel<T, AXPBY, SEARCH>,
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        configured[dev & 63].store(true, std::memory_order_relaxed);
+    }
+    const int shift_v = (int)((reinterpret_cast<uintptr_t>(values) & 15) / sizeof(T));
+    const int shift_c = (int)((reinterpret_cast<uintptr_t>(col) & 15) / sizeof(int));
+    const int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
+    if (!SEARCH) {
+        dim3 sgrid((p.num_tiles + 1 + 127) / 128), sblock(128);
+        tile_search_kernel<<<sgrid, sblock, 0, stream>>>(row_offsets + 1, num_rows, num_nonzeros, C::TILE,
+                                                         p.num_tiles, coords, ticket);
+        int rc = post_launch("tile_search_kernel", sgrid, sblock, 0, stream, debug_sync);
+        if (rc) return rc;
+    } else if (p.num_blocks > 1) {
+        MSPMV_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));  // the temp blob arrives uninitialised
+    }
+    dim3 grid(p.num_blocks), block(C::THREADS);
+    spmv_pipe_kernel<T, AXPBY, SEARCH><<<grid, block, smem, stream>>>(
+        values, row_offsets, col, x, y, coords, coords_out, carry_rows, carry_vals, ticket, alpha, beta, num_rows,
+        num_nonzeros, p.num_tiles, shift_v, shift_c, shift_r);
+    return post_launch("spmv_pipe_kernel", grid, block, smem, stream, debug_sync);
+}
+
 template <typename T, bool AXPBY>
 static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int* row_offsets,
                         const int* col, const T* x, T* y, int num_rows, int num_nonzeros, T alpha,
@@ -196,6 +290,16 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     T* carry_vals = reinterpret_cast<T*>(temp + p.off_carry_vals);
     const int* row_end = row_offsets + 1;  // device_spmv.cuh:148
 
+    if (p.engine == Engine::Pipe) {
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(temp + p.off_ticket);
+        if (pipe_search())
+            return pipe_launch_impl<T, AXPBY, true>(p, coords, nullptr, carry_rows, carry_vals, ticket, values,
+                                                    row_offsets, col, x, y, num_rows, num_nonzeros, alpha, beta,
+                                                    stream, debug_sync);
+        return pipe_launch_impl<T, AXPBY, false>(p, coords, nullptr, carry_rows, carry_vals, ticket, values,
+                                                 row_offsets, col, x, y, num_rows, num_nonzeros, alpha, beta, stream,
+                                                 debug_sync);
+    }
     if (p.engine == Engine::Stream) {
         int rc = stream_launch<T, AXPBY>(p.geom, values, row_offsets, col, x, y, num_rows,
                                          num_nonzeros, coords, carry_rows, carry_vals, alpha, beta,
@@ -449,13 +553,13 @@ int mspmv_csrmv_swath_coords(const int* d_row_offsets, int num_rows, int num_non
         int rc = make_plan<double>(num_rows, num_nonzeros, p);
         if (rc) return rc;
         n = p.num_tiles;
-        per = p.engine == Engine::Stream ? p.geom.swath_items : TileCfg<double>::TILE;
+        per = p.engine == Engine::Stream ? p.geom.swath_items : p.engine == Engine::Pipe ? PipeCfg<double>::TILE : TileCfg<double>::TILE;
     } else {
         Plan<float> p;
         int rc = make_plan<float>(num_rows, num_nonzeros, p);
         if (rc) return rc;
         n = p.num_tiles;
-        per = p.engine == Engine::Stream ? p.geom.swath_items : TileCfg<float>::TILE;
+        per = p.engine == Engine::Stream ? p.geom.swath_items : p.engine == Engine::Pipe ? PipeCfg<float>::TILE : TileCfg<float>::TILE;
     }
     *num_swaths = n;
     if (!d_coords) return 0;
@@ -681,7 +785,13 @@ int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out
         Plan<T> p;
         int rc = make_plan<T>(num_rows, num_nonzeros, p);
         if (rc) return rc;
-        if (p.engine == Engine::Stream) {
+        if (p.engine == Engine::Pipe) {
+            out[0] = p.num_blocks;
+            out[1] = PipeCfg<T>::THREADS;
+            out[2] = PipeCfg<T>::TILE;
+            out[3] = (int)pipe_smem_bytes<T>();
+            out[4] = pipe_search() ? 1 : 2;
+        } else if (p.engine == Engine::Stream) {
             out[0] = p.geom.num_swaths;
             out[1] = p.geom.threads;
             out[2] = p.geom.tile_items;
@@ -707,6 +817,7 @@ int mspmv_set_engine(const char* name)
     if (!std::strcmp(name, "auto")) g_engine_override = -1;
     else if (!std::strcmp(name, "tile")) g_engine_override = (int)Engine::Tile;
     else if (!std::strcmp(name, "stream")) g_engine_override = (int)Engine::Stream;
+    else if (!std::strcmp(name, "pipe")) g_engine_override = (int)Engine::Pipe;
     else return 1;
     return 0;
 }
@@ -721,6 +832,18 @@ int mspmv_set_option(const char* name, int value)
     if (!std::strcmp(name, "tile_variant")) {
         if (value != -1 && value != 0 && value != 2 && value != 3) return 1;
         g_tile_variant = value;  // -1: back to the environment / default
+        return 0;
+    }
+    if (!std::strcmp(name, "pipe_search")) {
+        g_pipe_search = value < 0 ? -1 : (value != 0);
+        return 0;
+    }
+    if (!std::strcmp(name, "pipe_blocks_per_sm")) {
+        g_pipe_blocks_per_sm = value < 0 ? -1 : value;
+        return 0;
+    }
+    if (!std::strcmp(name, "pipe_smem_kb")) {
+        g_pipe_smem_kb = value <= 0 ? -1 : value;
         return 0;
     }
     if (!std::strcmp(name, "auto_v3_max_row_items")) {

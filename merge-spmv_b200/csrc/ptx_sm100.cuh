@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 // the block's dynamic shared memory (one spelling for nvcc, another for the CPU interpreter)
-#define MSPMV_DYNAMIC_SHARED(name) extern __shared__ unsigned char name[]
+#define MSPMV_DYNAMIC_SHARED(name) extern __shared__ __align__(128) unsigned char name[]
 
 namespace mspmv {
 

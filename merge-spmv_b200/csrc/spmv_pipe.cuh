@@ -1,0 +1,390 @@
+// spmv_pipe.cuh -- "pipe" engine: ONE launch per CsrMV.  Persistent threadblocks, each owning a
+// contiguous run of equal-length diagonal swaths ("tiles") of the (row_end_offsets (+) N_nnz) merge
+// path, fed by a TMA pipeline.
+//
+// What one call does (the reference needs three launches: search, spmv, fix-up --
+// dispatch_spmv_orig.cuh:665-745):
+//   * grid = min(tiles, SMs x resident blocks); block b owns tiles [b*T/G, (b+1)*T/G).
+//   * warp 4 of every block is the PRODUCER.  It walks the block's piece of the merge path itself:
+//     the run's start coordinate by a warp-cooperative 32-ary MergePathSearch over the whole matrix
+//     (thread_search.cuh:53-84, same unique coordinate), every further tile boundary by a 32-ary
+//     search bounded to the <= TILE rows the tile can span (2-3 dependent L2 trips, off the
+//     consumers' critical path) -- this replaces DeviceSpmvSearchKernel
+//     (dispatch_spmv_orig.cuh:104-143).  For each tile it issues three cp.async.bulk copies (TMA,
+//     SASS UBLKCP): the tile's values, column indices and row-offset slice, into one stage of a
+//     shared-memory ring, completing on that stage's `full` mbarrier.
+//   * warps 0-3 are the CONSUMERS (all of them compute; there is no gather/reduce specialisation).
+//     Per tile, with nnzs nonzeros and nrows row ends:
+//       P1  row owners (thread r <-> row r of the tile) set bit (row_end[r] - y0) of a bitmap: a
+//           row boundary lies in front of that nonzero slot (slot nnzs = boundary at the tile's end);
+//       W   every thread owns IPT consecutive nonzero SLOTS: reads its flag bits, its column
+//           indices (shared memory), gathers x[col] (LDG, cache-hinted), then walks its slots:
+//           running = fma(value, x, running); at a flagged slot the finished segment sum is parked
+//           IN PLACE (the slot's own value is already in a register) and the sum restarts
+//           (the merge walk of agent_spmv_orig.cuh:557-578 without per-item row bookkeeping);
+//       S   one warp-shuffle segmented scan of (had a boundary, tail sum) per thread
+//           (ReduceByKeyOp, thread_operators.cuh:278-302) gives every thread the partial that
+//           precedes it -- added to its first parked segment -- and the tile's carry-out, which
+//           stays in registers for the block's next tile;
+//       Y   row owners read their row's parked sum and store y, coalesced (empty rows get 0).
+//     P1 of tile i+1 runs before the barrier that ends S of tile i, so a tile costs two
+//     128-thread named barriers.  The stage is handed back to the producer through its `empty`
+//     mbarrier.
+//   * a block's last carry-out (row, partial) goes to global memory; the last block to finish
+//     (ticket) folds the G carries into y in carry order -- the serial loop of
+//     cpu_spmv.cpp:348-352, guard row < num_rows -- replacing DeviceSegmentFixupKernel
+//     (dispatch_spmv_orig.cuh:199-224).  No floating-point atomics: same bits every run.
+#pragma once
+
+#include <limits.h>
+
+#include "merge_common.cuh"
+#include "tma_stage.cuh"
+
+namespace mspmv {
+
+#ifndef MSPMV_PIPE_IPT
+#define MSPMV_PIPE_IPT (sizeof(T) == 8 ? 9 : 13)
+#endif
+#ifndef MSPMV_PIPE_STAGES
+#define MSPMV_PIPE_STAGES 2   // slots of the value / row-offset ring
+#endif
+#ifndef MSPMV_PIPE_CSTAGES
+#define MSPMV_PIPE_CSTAGES 2  // slots of the column-index ring
+#endif
+#ifndef MSPMV_PIPE_CONSUMER_WARPS
+#define MSPMV_PIPE_CONSUMER_WARPS 4
+#endif
+
+template <typename T>
+struct PipeCfg {
+    static constexpr int NW = MSPMV_PIPE_CONSUMER_WARPS;  // consumer warps
+    static constexpr int CONSUMERS = NW * 32;
+    static constexpr int THREADS = CONSUMERS + 32;         // + the producer warp
+    static constexpr int IPT = MSPMV_PIPE_IPT;             // nonzero slots per consumer thread (odd: conflict-free strided LDS)
+    static constexpr int TILE = CONSUMERS * IPT;           // merge items per tile
+    static constexpr int STAGES = MSPMV_PIPE_STAGES;
+    static constexpr int CSTAGES = MSPMV_PIPE_CSTAGES;
+    static constexpr int BW = TILE / 32 + 2;               // bitmap words (slot TILE is never flagged; +1 for the funnel shift)
+    static constexpr int ROWCAP = 384;                     // row offsets staged per tile; tiles with more rows read them through L2
+    static constexpr int GV = 16 / (int)sizeof(T);
+    static constexpr int LOCAL_SPAN = 32768;               // see spmv_tile.cuh: L1 policy of the gathers
+    static_assert(IPT >= 2 && IPT < 32 && BW <= CONSUMERS, "bitmap layout");
+};
+
+// Two rings, because the two halves of a tile are needed at different times: the column indices
+// only until the tile's gathers have been issued (one tile AHEAD of the walk), the values and row
+// offsets until its rows have been stored.
+template <typename T>
+struct alignas(128) PipeStage {
+    using C = PipeCfg<T>;
+    T val[C::TILE + 2 * C::GV];  // staged values; a flagged slot later holds its parked segment sum
+    int row[C::ROWCAP + 8];
+};
+template <typename T>
+struct alignas(128) PipeColStage {
+    int col[PipeCfg<T>::TILE + 8];
+};
+
+template <typename T>
+struct alignas(128) PipeCtl {
+    using C = PipeCfg<T>;
+    uint64_t full[C::STAGES];    // values + row offsets of a tile have landed
+    uint64_t empty[C::STAGES];
+    uint64_t full_c[C::CSTAGES];  // column indices of a tile have landed
+    uint64_t empty_c[C::CSTAGES];
+    int4 coord[C::CSTAGES];      // (x0, y0, x1, y1) of the tile in the column slot (read once, kept in registers)
+    uint32_t bits[2][C::BW];
+    Seg<T> warp[C::NW];
+    int last;
+};
+
+template <typename T>
+constexpr size_t pipe_smem_bytes()
+{
+    return sizeof(PipeCtl<T>) + sizeof(PipeStage<T>) * PipeCfg<T>::STAGES +
+           sizeof(PipeColStage<T>) * PipeCfg<T>::CSTAGES;
+}
+
+// 32-ary warp search for the coordinate on diagonal `diag`, x known to lie in [lo, hi].
+__device__ __forceinline__ int2 warp_merge_path_search_bounded(int diag, const int* __restrict__ row_end_offsets,
+                                                               int num_rows, int lo, int hi, int lane)
+{
+    while (lo < hi) {
+        const int span = hi - lo;
+        int pivot = lo + (int)(((int64_t)span * (lane + 1)) / 33);
+        pivot = min(pivot, hi - 1);
+        const bool go_up = __ldg(row_end_offsets + pivot) <= diag - pivot - 1;  // monotone in pivot
+        const unsigned up = __ballot_sync(kFull, go_up);
+        const int n_up = __popc(up);
+        const int new_lo = n_up > 0 ? __shfl_sync(kFull, pivot, n_up - 1) + 1 : lo;
+        const int new_hi = n_up < 32 ? __shfl_sync(kFull, pivot, n_up) : hi;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    return make_int2(min(lo, num_rows), diag - lo);
+}
+
+template <typename T, bool AXPBY, bool SEARCH>
+__global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
+    const T* __restrict__ values, const int* __restrict__ row_offsets,
+    const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
+    const int2* __restrict__ coords_in,  // !SEARCH: tile coordinates from tile_search_kernel
+    int2* __restrict__ coords_out,       // optional export of the coordinates the producer found
+    int* __restrict__ carry_rows, T* __restrict__ carry_vals, unsigned int* __restrict__ ticket, T alpha, T beta,
+    int num_rows, int num_nonzeros, int num_tiles, int shift_v, int shift_c, int shift_r)
+{
+    using C = PipeCfg<T>;
+    constexpr int IPT = C::IPT, NW = C::NW, STAGES = C::STAGES, CSTAGES = C::CSTAGES, GV = C::GV;
+    MSPMV_DYNAMIC_SHARED(smem_raw);
+    PipeCtl<T>& ctl = *reinterpret_cast<PipeCtl<T>*>(smem_raw);
+    PipeStage<T>* stages = reinterpret_cast<PipeStage<T>*>(smem_raw + sizeof(PipeCtl<T>));
+    PipeColStage<T>* cstages =
+        reinterpret_cast<PipeColStage<T>*>(smem_raw + sizeof(PipeCtl<T>) + sizeof(PipeStage<T>) * STAGES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x;
+    const int t0 = (int)(((int64_t)blockIdx.x * num_tiles) / G);
+    const int t1 = (int)(((int64_t)(blockIdx.x + 1) * num_tiles) / G);
+    const int n = t1 - t0;  // >= 1: the host launches at most num_tiles blocks
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&ctl.full[s], 1);
+            mbar_init(&ctl.empty[s], NW);
+        }
+#pragma unroll
+        for (int s = 0; s < CSTAGES; ++s) {
+            mbar_init(&ctl.full_c[s], 1);
+            mbar_init(&ctl.empty_c[s], NW);
+        }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 2 * C::BW; i += C::THREADS) (&ctl.bits[0][0])[i] = 0u;
+    __syncthreads();
+
+    // =============================== producer warp ================================================
+    if (warp == NW) {
+        const uint64_t policy = l2_policy_evict_first();
+        const int* row_end = row_offsets + 1;  // device_spmv.cuh:148
+        const int64_t total = (int64_t)num_rows + num_nonzeros;
+        int2 c0;
+        if (SEARCH)
+            c0 = warp_merge_path_search_global((int64_t)t0 * C::TILE, row_end, num_rows, num_nonzeros, lane);
+        else
+            c0 = __ldg(coords_in + t0);
+        for (int i = 0; i < n; ++i) {
+            const int s = i % STAGES, sc = i % CSTAGES;
+            int2 c1;
+            if (SEARCH) {
+                const int64_t d64 = (int64_t)(t0 + i + 1) * C::TILE;
+                const int d1 = (int)(d64 < total ? d64 : total);
+                // the path is monotone: x1 in [x0, x0 + (d1 - d0)] = [x0, d1 - y0]
+                c1 = warp_merge_path_search_bounded(d1, row_end, num_rows, max(c0.x, d1 - num_nonzeros),
+                                                    min(d1 - c0.y, num_rows), lane);
+            } else {
+                c1 = __ldg(coords_in + t0 + i + 1);
+            }
+            if (coords_out != nullptr && lane == 0) {
+                coords_out[t0 + i] = c0;
+                if (t0 + i + 1 == num_tiles) coords_out[num_tiles] = c1;
+            }
+            const int x0 = c0.x, y0 = c0.y, nrows = c1.x - c0.x, nnzs = c1.y - c0.y;
+            // column indices first: the consumers gather for this tile one tile ahead of its walk
+            if (i >= CSTAGES) mbar_wait(&ctl.empty_c[sc], (uint32_t)((i / CSTAGES) - 1) & 1u);
+            const int base_c = (y0 + shift_c) & ~3;
+            uint32_t b = stage_superset<int>(column_indices, shift_c, y0, y0 + nnzs, num_nonzeros, cstages[sc].col,
+                                             base_c, &ctl.full_c[sc], policy, lane);
+            if (lane == 0) ctl.coord[sc] = make_int4(c0.x, c0.y, c1.x, c1.y);
+            __syncwarp();
+            if (lane == 0) {
+                if (b) mbar_arrive_expect_tx(&ctl.full_c[sc], b);
+                else mbar_arrive(&ctl.full_c[sc]);
+            }
+            if (i >= STAGES) mbar_wait(&ctl.empty[s], (uint32_t)((i / STAGES) - 1) & 1u);
+            PipeStage<T>& st = stages[s];
+            const int base_v = (y0 + shift_v) & ~(GV - 1);
+            const int jr0 = x0 + 1;  // row_end_offsets[x0 + r] == row_offsets[jr0 + r]
+            const int base_r = (jr0 + shift_r) & ~3;
+            b = stage_superset<T>(values, shift_v, y0, y0 + nnzs, num_nonzeros, st.val, base_v, &ctl.full[s], policy,
+                                  lane);
+            if (nrows <= C::ROWCAP)
+                b += stage_superset<int>(row_offsets, shift_r, jr0, jr0 + nrows, num_rows + 1, st.row, base_r,
+                                         &ctl.full[s], policy, lane);
+            __syncwarp();
+            if (lane == 0) {
+                if (b) mbar_arrive_expect_tx(&ctl.full[s], b);
+                else mbar_arrive(&ctl.full[s]);
+            }
+            c0 = c1;
+        }
+        return;
+    }
+
+    // =============================== consumer warps ===============================================
+    // P1: row owners flag the slot in front of which their row ends
+    auto mark_rows = [&](const int4 c, const PipeStage<T>& st, uint32_t* bits) {
+        const int nrows = c.z - c.x, jr0 = c.x + 1;
+        const int off_r = (jr0 + shift_r) & 3;
+        for (int r = tid; r < nrows; r += C::CONSUMERS) {
+            const int e = nrows <= C::ROWCAP ? st.row[off_r + r] : __ldg(row_offsets + jr0 + r);
+            const int pos = e - c.y;
+            atomicOr(&bits[pos >> 5], 1u << (pos & 31));
+        }
+    };
+
+    const uint64_t keep = l2_policy_evict_last();  // x is the only reused data: keep it in L2
+    const int base = tid * IPT;  // my first slot
+
+    // G: read my column indices of tile k and issue the x gathers; the values come back while the
+    // PREVIOUS tile is walked, scanned and stored (the loads are only consumed one step later).
+    auto gather = [&](int k, const int4 c, T(&xo)[IPT]) {
+        const int sc = k % CSTAGES;
+        const int nnzs = c.w - c.y;
+        const int n_mine = min(max(nnzs - base, 0), IPT);  // my slots that hold a nonzero
+        const int* pc = cstages[sc].col + (((c.y + shift_c) & 3) + base);
+        int cidx[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) cidx[j] = j < n_mine ? pc[j] : -1;
+        // L1 policy per warp by column span (spmv_tile.cuh): narrow span = lines are re-used
+        int cmin = cidx[0] >= 0 ? cidx[0] : INT_MAX, cmax = cidx[0];
+        if (cidx[IPT - 1] >= 0) {
+            cmin = min(cmin, cidx[IPT - 1]);
+            cmax = max(cmax, cidx[IPT - 1]);
+        }
+        cmin = __reduce_min_sync(kFull, cmin);
+        cmax = __reduce_max_sync(kFull, cmax);
+        if (cmax - cmin < C::LOCAL_SPAN) {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) xo[j] = cidx[j] >= 0 ? ld_gather_l1(x + cidx[j], keep) : T(0);
+        } else {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) xo[j] = cidx[j] >= 0 ? ld_gather(x + cidx[j], keep) : T(0);
+        }
+        __syncwarp();  // every lane's indices have been consumed by its gathers: hand the slot back
+        if (lane == 0) mbar_arrive(&ctl.empty_c[sc]);
+    };
+
+    Seg<T> carry;  // the row that continues from this block's previous tile
+    carry.val = T(0);
+    carry.ended = 0;
+    int4 cur, nxt;
+    T xa[IPT], xb[IPT];
+    mbar_wait(&ctl.full_c[0], 0);
+    cur = ctl.coord[0];
+    gather(0, cur, xa);
+    mbar_wait(&ctl.full[0], 0);
+    mark_rows(cur, stages[0], ctl.bits[0]);
+    nxt = cur;
+    named_bar_sync(2, C::CONSUMERS);
+
+    // one tile: xc = the x values gathered for it one step ago, xn = where the next tile's go
+    auto step = [&](int i, T(&xc)[IPT], T(&xn)[IPT]) {
+        const int s = i % STAGES, bsel = i & 1;
+        PipeStage<T>& st = stages[s];
+        if (i + 1 < n) {
+            const int sc1 = (i + 1) % CSTAGES;
+            mbar_wait(&ctl.full_c[sc1], (uint32_t)((i + 1) / CSTAGES) & 1u);
+            nxt = ctl.coord[sc1];
+            gather(i + 1, nxt, xn);
+        }
+        const int x0 = cur.x, y0 = cur.y, nrows = cur.z - cur.x, nnzs = cur.w - cur.y;
+        const int off_v = (y0 + shift_v) & (GV - 1);
+        const int n_mine = min(max(nnzs - base, 0), IPT);
+
+        // ---- W: my flag bits, then walk my slots (cpu_spmv.cpp:324-340) ----------------------------
+        const uint32_t w0 = ctl.bits[bsel][base >> 5], w1 = ctl.bits[bsel][(base >> 5) + 1];
+        const uint32_t bits = __funnelshift_r(w0, w1, base & 31) & ((1u << IPT) - 1u);
+        T running = T(0);
+        {
+            T* pv = st.val + (off_v + base);
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const T v = j < n_mine ? pv[j] : T(0);
+                if ((bits >> j) & 1u) {  // a row ends in front of slot j: park its sum, start over
+                    pv[j] = running;
+                    running = T(0);
+                }
+                running = fma(v, xc[j], running);
+            }
+        }
+        // ---- S: block-wide segmented scan of (had a boundary, tail sum) ----------------------------
+        Seg<T> elem, excl, total;
+        elem.val = running;
+        elem.ended = bits != 0u;
+        block_seg_scan_exclusive<T, NW, true>(elem, carry, ctl.warp, tid, 1, excl, total);
+        if (bits != 0u) st.val[off_v + base + (__ffs((int)bits) - 1)] += excl.val;  // my first parked segment
+        if (tid < C::BW) ctl.bits[bsel][tid] = 0u;  // everybody read its bits before the scan's barrier
+        carry.val = total.val;
+
+        // ---- P1 of the next tile, then the barrier that publishes the parked sums -----------------
+        if (i + 1 < n) {
+            const int s1 = (i + 1) % STAGES;
+            mbar_wait(&ctl.full[s1], (uint32_t)((i + 1) / STAGES) & 1u);
+            mark_rows(nxt, stages[s1], ctl.bits[bsel ^ 1]);
+        }
+        named_bar_sync(2, C::CONSUMERS);
+
+        // ---- Y: row owners store y ----------------------------------------------------------------
+        {
+            const int jr0 = x0 + 1;
+            const int off_r = (jr0 + shift_r) & 3;
+            for (int r = tid; r < nrows; r += C::CONSUMERS) {
+                int e, ep;
+                if (nrows <= C::ROWCAP) {
+                    e = st.row[off_r + r];
+                    ep = r > 0 ? st.row[off_r + r - 1] : e - 1;
+                } else {
+                    e = __ldg(row_offsets + jr0 + r);
+                    ep = r > 0 ? __ldg(row_offsets + jr0 + r - 1) : e - 1;
+                }
+                const T sum = ep != e ? st.val[off_v + (e - y0)] : T(0);  // ep == e: empty row
+                y[x0 + r] = epilogue<T, AXPBY>(sum, alpha, beta, y + x0 + r);
+            }
+        }
+        // hand the stage back: my generic-proxy accesses are ordered before the producer's next bulk copy
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl.empty[s]);
+        cur = nxt;
+    };
+    for (int i = 0; i < n; i += 2) {  // ping-pong register sets: no copy waits for the gathers in flight
+        step(i, xa, xb);
+        if (i + 1 < n) step(i + 1, xb, xa);
+    }
+
+    // ---- the run's carry-out; the last block to finish folds all of them (cpu_spmv.cpp:348-352) ---
+    if (tid == 0) {
+        carry_rows[blockIdx.x] = cur.z;  // may equal num_rows: dropped by the fold
+        carry_vals[blockIdx.x] = carry.val;
+    }
+    if (G == 1) return;  // dispatch_spmv_orig.cuh:721
+    __threadfence();
+    named_bar_sync(2, C::CONSUMERS);
+    if (tid == 0) ctl.last = atomicAdd(ticket, 1u) == (unsigned)G - 1u;
+    named_bar_sync(2, C::CONSUMERS);
+    if (!ctl.last) return;
+    __threadfence();
+    Seg<T> run;  // the run of equal rows that touches the end of the previous chunk
+    run.val = T(0);
+    run.ended = 0;
+    for (int base = 0; base < G; base += C::CONSUMERS) {
+        const int i = base + tid;
+        const int row = i < G ? carry_rows[i] : INT_MAX;
+        const int prev_row = (i > 0 && i < G) ? carry_rows[i - 1] : -1;
+        const int next_row = i + 1 < G ? carry_rows[i + 1] : INT_MAX;
+        Seg<T> e, excl, total;
+        e.val = i < G ? carry_vals[i] : T(0);
+        e.ended = row != prev_row;  // a new run starts here
+        block_seg_scan_exclusive<T, NW, false>(e, run, ctl.warp, tid, 1, excl, total);
+        const T run_sum = e.ended ? e.val : excl.val + e.val;  // my run up to and including me
+        if (i < G && row != next_row && row < num_rows) y[row] += AXPBY ? alpha * run_sum : run_sum;
+        run.val = total.val;
+        run.ended = 0;
+        named_bar_sync(2, C::CONSUMERS);  // ctl.warp is reused by the next chunk
+    }
+}
+
+}  // namespace mspmv

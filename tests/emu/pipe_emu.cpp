@@ -1,0 +1,94 @@
+// pipe_emu.cpp -- runs the pipe engine's kernel (merge-spmv_b200/csrc/spmv_pipe.cuh, compiled unchanged)
+// under the host SIMT interpreter.  TEST INFRASTRUCTURE ONLY: built by tests/test_pipe_emu.py, never part
+// of the product.  The launch mirrors pipe_launch_impl() in merge-spmv_b200/csrc/mergespmv.cu: a 4-byte
+// memset of the ticket (or tile_search_kernel when search == 0), then ONE kernel.
+#define MSPMV_PTX_HEADER "ptx_emu.cuh"
+#include "simt_emu.hpp"
+
+#include "spmv_tile.cuh"  // tile_search_kernel, diagonal_search_kernel
+#include "spmv_pipe.cuh"
+
+#include <vector>
+
+namespace {
+
+using namespace mspmv;
+
+template <typename T>
+int shift_of(const void* p)
+{
+    return (int)((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
+}
+
+template <typename T, bool AXPBY>
+int run(const T* values, const int* row_offsets, const int* col, const T* x, T* y, int num_rows, int num_nonzeros,
+        T alpha, T beta, int max_blocks, int search, int* coords_out, int* stats)
+{
+    using C = PipeCfg<T>;
+    if (num_rows <= 0) return 0;
+    const int64_t merge_items = (int64_t)num_rows + num_nonzeros;
+    const int num_tiles = (int)((merge_items + C::TILE - 1) / C::TILE);
+    const int num_blocks = num_tiles < max_blocks ? num_tiles : max_blocks;
+    // temporaries of exactly the size the kernel may touch, filled with garbage (the temp blob is uninitialised)
+    std::vector<int2> coords_buf((size_t)num_tiles + 1);
+    std::vector<int> cr_buf((size_t)num_blocks);
+    std::vector<T> cv_buf((size_t)num_blocks);
+    std::memset(coords_buf.data(), 0xEE, coords_buf.size() * sizeof(int2));
+    std::memset(cr_buf.data(), 0xEE, cr_buf.size() * sizeof(int));
+    std::memset(cv_buf.data(), 0xEE, cv_buf.size() * sizeof(T));
+    unsigned int ticket = 0xEEEEEEEEu;
+    if (stats) {
+        stats[0] = num_tiles;
+        stats[1] = C::TILE;
+        stats[2] = C::THREADS;
+        stats[3] = num_blocks;
+    }
+    if (!search) {
+        emu::launch((unsigned)((num_tiles + 1 + 127) / 128), 128, [&] {
+            tile_search_kernel(row_offsets + 1, num_rows, num_nonzeros, C::TILE, num_tiles, coords_buf.data(), &ticket);
+        });
+    } else {
+        ticket = 0u;  // cudaMemsetAsync
+    }
+    int2* cout = reinterpret_cast<int2*>(coords_out);
+    emu::launch((unsigned)num_blocks, (unsigned)C::THREADS, [&] {
+        if (search)
+            spmv_pipe_kernel<T, AXPBY, true>(values, row_offsets, col, x, y, nullptr, cout, cr_buf.data(), cv_buf.data(),
+                                             &ticket, alpha, beta, num_rows, num_nonzeros, num_tiles,
+                                             shift_of<T>(values), shift_of<int>(col), shift_of<int>(row_offsets));
+        else
+            spmv_pipe_kernel<T, AXPBY, false>(values, row_offsets, col, x, y, coords_buf.data(), cout, cr_buf.data(),
+                                              cv_buf.data(), &ticket, alpha, beta, num_rows, num_nonzeros, num_tiles,
+                                              shift_of<T>(values), shift_of<int>(col), shift_of<int>(row_offsets));
+    });
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_pipe_f64(const double* v, const int* ro, const int* ci, const double* x, double* y, int rows, int nnz,
+                 double alpha, double beta, int axpby, int max_blocks, int search, int* coords_out, int* stats)
+{
+    return axpby ? run<double, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, max_blocks, search, coords_out, stats)
+                 : run<double, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, max_blocks, search, coords_out, stats);
+}
+int emu_pipe_f32(const float* v, const int* ro, const int* ci, const float* x, float* y, int rows, int nnz, float alpha,
+                 float beta, int axpby, int max_blocks, int search, int* coords_out, int* stats)
+{
+    return axpby ? run<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, max_blocks, search, coords_out, stats)
+                 : run<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, max_blocks, search, coords_out, stats);
+}
+
+// thread resume order inside a block: 0 ascending, 1 descending, 2 random per pass
+void emu_set_schedule(int mode) { emu::set_schedule(mode); }
+
+int emu_merge_path_search(const int* ro, int rows, int nnz, const int* diagonals, int n, int* coords)
+{
+    emu::launch((unsigned)((n + 127) / 128), 128, [&] {
+        diagonal_search_kernel(ro + 1, rows, nnz, diagonals, n, reinterpret_cast<int2*>(coords));
+    });
+    return 0;
+}
+}

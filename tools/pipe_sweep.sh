@@ -1,0 +1,35 @@
+#!/usr/bin/env bash
+# Round-2 timing sweep of the pipe engine (csrc/spmv_pipe.cuh) against the round-1 tile engine.
+#   gpurun --timeout 1500 -- 'bash tools/pipe_sweep.sh'
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out
+mkdir -p "$OUT"
+PY=python
+STEPS=${STEPS:-200}
+LOG="$OUT/pipe_sweep.txt"
+: > "$LOG"
+V=merge-spmv_b200/variants
+lib() {  # label, options, env assignments...
+    local label=$1; shift
+    local opts=$1; shift
+    env "$@" timeout 900 $PY tools/sweep_lib.py --label "$label" --steps "$STEPS" --options "$opts" ${WL:+--workloads "$WL"} > "$OUT/sweep_lib.log" 2>&1
+    if grep -qE "ms \|" "$OUT/sweep_lib.log"; then grep -E "^#|\|" "$OUT/sweep_lib.log" | tee -a "$LOG"
+    else echo "$label FAILED:" | tee -a "$LOG"; tail -12 "$OUT/sweep_lib.log" | tee -a "$LOG"; fi
+}
+if [ "${SKIP_TESTS:-0}" != 1 ]; then
+    echo "== gpu tests" | tee -a "$LOG"
+    timeout 1200 $PY -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee -a "$LOG"
+fi
+echo "== shipped build: tile engine (round 1) vs pipe engine" | tee -a "$LOG"
+lib shipped "engine=tile;engine=pipe;engine=pipe,pipe_search=0"
+echo "== pipe: compile-time variants" | tee -a "$LOG"
+for B in ${VARIANTS:-p_ipt7_11 p_ipt11_15 p_ipt5_9 p_st3 p_st3_ipt7_11 p_st3_ipt5_9 p_nw8 p_nw8_ipt5_7}; do
+    [ -f $V/libmergespmv_$B.so ] && lib $B "engine=pipe" MSPMV_LIB=$V/libmergespmv_$B.so
+done
+echo "== pipe: shared-memory budget per SM (rest is L1) / resident blocks" | tee -a "$LOG"
+for KB in ${SMEM_KBS:-96 128 192}; do lib "smem ${KB}KB" "engine=pipe" MSPMV_PIPE_SMEM_KB=$KB; done
+for KB in ${SMEM_KBS_ST3:-128 192}; do lib "p_st3_ipt7_11 smem ${KB}KB" "engine=pipe" MSPMV_PIPE_SMEM_KB=$KB MSPMV_LIB=$V/libmergespmv_p_st3_ipt7_11.so; done
+echo "== small matrix (config 1 shape)" | tee -a "$LOG"
+WL=cpu_uniform_16k STEPS=2000 lib "small" "engine=tile;engine=pipe"
+echo done | tee -a "$LOG"
