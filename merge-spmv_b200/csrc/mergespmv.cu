@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/mergespmv.h"
@@ -150,12 +151,77 @@ static int pipe_smem_kb()
     return env;
 }
 
+// Two instantiations of the pipe kernel per value type: A for matrices with long rows (the x gathers
+// dominate), B for short rows (row bookkeeping dominates).  <IPT fp64, IPT fp32, value-ring slots,
+// column-ring slots, gather-ahead, consumer warps>; overridable at build time for tuning sweeps.
+// (nvcc splits -D values at commas, hence one macro per field; PB_* default to PA_*)
+#ifndef PA_I64
+#define PA_I64 9
+#endif
+#ifndef PA_I32
+#define PA_I32 13
+#endif
+#ifndef PA_VST
+#define PA_VST 2
+#endif
+#ifndef PA_CST
+#define PA_CST 2
+#endif
+#ifndef PA_AHEAD
+#define PA_AHEAD 0
+#endif
+#ifndef PA_NW
+#define PA_NW 4
+#endif
+#ifndef PB_I64
+#define PB_I64 PA_I64
+#endif
+#ifndef PB_I32
+#define PB_I32 PA_I32
+#endif
+#ifndef PB_VST
+#define PB_VST PA_VST
+#endif
+#ifndef PB_CST
+#define PB_CST PA_CST
+#endif
+#ifndef PB_AHEAD
+#define PB_AHEAD PA_AHEAD
+#endif
+#ifndef PB_NW
+#define PB_NW PA_NW
+#endif
+#define MSPMV_PIPE_A PA_I64, PA_I32, PA_VST, PA_CST, PA_AHEAD, PA_NW
+#define MSPMV_PIPE_B PB_I64, PB_I32, PB_VST, PB_CST, PB_AHEAD, PB_NW
+#ifndef MSPMV_PIPE_B_MAX_ROW_ITEMS
+#define MSPMV_PIPE_B_MAX_ROW_ITEMS 16  // B when (rows + nnz) / rows <= this
+#endif
+template <typename T, int I64, int I32, int VST, int CST, int AHEAD, int NW>
+using PipeCfgSel = PipeCfg<T, (sizeof(T) == 8 ? I64 : I32), VST, CST, AHEAD, NW>;
 template <typename T>
+using PipeCfgA = PipeCfgSel<T, MSPMV_PIPE_A>;
+template <typename T>
+using PipeCfgB = PipeCfgSel<T, MSPMV_PIPE_B>;
+
+static std::atomic<int> g_pipe_config{-1};  // 0 = by shape, 1 = A, 2 = B
+static int pipe_config_for(int num_rows, int num_nonzeros)
+{
+    int v = g_pipe_config.load(std::memory_order_relaxed);
+    if (v < 0) {
+        static int env = env_int("MSPMV_PIPE_CONFIG", 0);
+        v = env;
+    }
+    if (v == 1 || v == 2) return v - 1;
+    const int64_t items = (int64_t)num_rows + num_nonzeros;
+    return (num_rows > 0 && items <= (int64_t)MSPMV_PIPE_B_MAX_ROW_ITEMS * num_rows) ? 1 : 0;
+}
+
+template <class C>
 static int pipe_blocks_per_sm()
 {
-    const int per_block = (int)pipe_smem_bytes<T>() + 1024;  // + the per-block reservation of the driver
+    const int per_block = (int)pipe_smem_bytes<C>() + 1024;  // + the per-block reservation of the driver
     int b = pipe_smem_kb() * 1024 / per_block;
-    const int by_threads = 2048 / PipeCfg<T>::THREADS;
+    const int by_threads = 2048 / C::THREADS;
     if (b > by_threads) b = by_threads;
     const int want = pipe_blocks_per_sm_opt();
     if (want > 0 && want < b) b = want;
@@ -171,6 +237,8 @@ struct Plan {
     int num_tiles;      // tile engine: tiles; stream engine: swaths (threadblocks)
     int num_fix_blocks;  // tile engine: level-1 fix-up blocks
     int num_blocks;      // pipe engine: threadblocks (each owns a contiguous run of tiles)
+    int pipe_cfg;        // pipe engine: 0 = PipeCfgA, 1 = PipeCfgB
+    int tile_items;      // merge items per tile of the chosen kernel
     size_t off_coords, off_carry_rows, off_carry_vals, off_carry2_rows, off_carry2_vals, off_ticket, bytes;
     StreamGeom geom;    // stream engine only
 };
@@ -186,9 +254,14 @@ static int make_plan(int num_rows, int num_nonzeros, Plan<T>& p)
     if (e == Engine::Auto) e = Engine::Pipe;
     p.engine = e;
     p.num_blocks = 0;
+    p.pipe_cfg = 0;
+    p.tile_items = TileCfg<T>::TILE;
     if (e == Engine::Pipe) {
-        p.num_tiles = (int)((p.merge_items + PipeCfg<T>::TILE - 1) / PipeCfg<T>::TILE);
-        const int resident = di.sm_count * pipe_blocks_per_sm<T>();
+        p.pipe_cfg = pipe_config_for(num_rows, num_nonzeros);
+        p.tile_items = p.pipe_cfg ? PipeCfgB<T>::TILE : PipeCfgA<T>::TILE;
+        p.num_tiles = (int)((p.merge_items + p.tile_items - 1) / p.tile_items);
+        const int resident =
+            di.sm_count * (p.pipe_cfg ? pipe_blocks_per_sm<PipeCfgB<T>>() : pipe_blocks_per_sm<PipeCfgA<T>>());
         p.num_blocks = p.num_tiles < resident ? p.num_tiles : resident;
     } else if (e == Engine::Stream) {
         p.geom = stream_geometry<T>(p.merge_items, di.sm_count);
@@ -241,23 +314,25 @@ static int tile_prefetch_ahead()
     return di.sm_count * 11;
 }
 
-template <typename T, bool AXPBY, bool SEARCH>
-static int pipe_launch_impl(const Plan<T>& p, int2* coords, int2* coords_out, int* carry_rows, T* carry_vals,
-                            unsigned int* ticket, const T* values, const int* row_offsets, const int* col,
-                            const T* x, T* y, int num_rows, int num_nonzeros, T alpha, T beta,
-                            cudaStream_t stream, int debug_sync)
+template <class C, bool AXPBY, bool SEARCH>
+static int pipe_launch_impl(const Plan<typename C::value_type>& p, int2* coords, int2* coords_out, int* carry_rows,
+                            typename C::value_type* carry_vals,
+                            unsigned int* ticket, const typename C::value_type* values, const int* row_offsets,
+                            const int* col, const typename C::value_type* x, typename C::value_type* y,
+                            int num_rows, int num_nonzeros, typename C::value_type alpha,
+                            typename C::value_type beta, cudaStream_t stream, int debug_sync)
 {
-    using C = PipeCfg<T>;
-    constexpr size_t smem = pipe_smem_bytes<T>();
+    using T = typename C::value_type;
+    constexpr size_t smem = pipe_smem_bytes<C>();
     static std::atomic<bool> configured[64];  // per device; a benign race only repeats the calls
     int dev = 0;
     MSPMV_TRY(cudaGetDevice(&dev));
     if (!configured[dev & 63].load(std::memory_order_relaxed)) {
-        MSPMV_TRY(cudaFuncSetAttribute(spmv_pipe_kernel<T, AXPBY, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MSPMV_TRY(cudaFuncSetAttribute(spmv_pipe_kernel<C, AXPBY, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         int pct = (pipe_smem_kb() * 100 + 227) / 228;
         if (pct > 100) pct = 100;
-        MSPMV_TRY(cudaFuncSetAttribute(spmv_pipe_kernel<T, AXPBY, SEARCH>,
+        MSPMV_TRY(cudaFuncSetAttribute(spmv_pipe_kernel<C, AXPBY, SEARCH>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         configured[dev & 63].store(true, std::memory_order_relaxed);
     }
@@ -274,7 +349,7 @@ static int pipe_launch_impl(const Plan<T>& p, int2* coords, int2* coords_out, in
         MSPMV_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));  // the temp blob arrives uninitialised
     }
     dim3 grid(p.num_blocks), block(C::THREADS);
-    spmv_pipe_kernel<T, AXPBY, SEARCH><<<grid, block, smem, stream>>>(
+    spmv_pipe_kernel<C, AXPBY, SEARCH><<<grid, block, smem, stream>>>(
         values, row_offsets, col, x, y, coords, coords_out, carry_rows, carry_vals, ticket, alpha, beta, num_rows,
         num_nonzeros, p.num_tiles, shift_v, shift_c, shift_r);
     return post_launch("spmv_pipe_kernel", grid, block, smem, stream, debug_sync);
@@ -292,13 +367,15 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
 
     if (p.engine == Engine::Pipe) {
         unsigned int* ticket = reinterpret_cast<unsigned int*>(temp + p.off_ticket);
-        if (pipe_search())
-            return pipe_launch_impl<T, AXPBY, true>(p, coords, nullptr, carry_rows, carry_vals, ticket, values,
-                                                    row_offsets, col, x, y, num_rows, num_nonzeros, alpha, beta,
-                                                    stream, debug_sync);
-        return pipe_launch_impl<T, AXPBY, false>(p, coords, nullptr, carry_rows, carry_vals, ticket, values,
-                                                 row_offsets, col, x, y, num_rows, num_nonzeros, alpha, beta, stream,
-                                                 debug_sync);
+        auto go = [&](auto cfg, auto search) {
+            using C = decltype(cfg);
+            return pipe_launch_impl<C, AXPBY, decltype(search)::value>(p, coords, nullptr, carry_rows, carry_vals, ticket,
+                                                                       values, row_offsets, col, x, y, num_rows,
+                                                                       num_nonzeros, alpha, beta, stream, debug_sync);
+        };
+        if (p.pipe_cfg)
+            return pipe_search() ? go(PipeCfgB<T>(), std::true_type()) : go(PipeCfgB<T>(), std::false_type());
+        return pipe_search() ? go(PipeCfgA<T>(), std::true_type()) : go(PipeCfgA<T>(), std::false_type());
     }
     if (p.engine == Engine::Stream) {
         int rc = stream_launch<T, AXPBY>(p.geom, values, row_offsets, col, x, y, num_rows,
@@ -553,13 +630,13 @@ int mspmv_csrmv_swath_coords(const int* d_row_offsets, int num_rows, int num_non
         int rc = make_plan<double>(num_rows, num_nonzeros, p);
         if (rc) return rc;
         n = p.num_tiles;
-        per = p.engine == Engine::Stream ? p.geom.swath_items : p.engine == Engine::Pipe ? PipeCfg<double>::TILE : TileCfg<double>::TILE;
+        per = p.engine == Engine::Stream ? p.geom.swath_items : p.tile_items;
     } else {
         Plan<float> p;
         int rc = make_plan<float>(num_rows, num_nonzeros, p);
         if (rc) return rc;
         n = p.num_tiles;
-        per = p.engine == Engine::Stream ? p.geom.swath_items : p.engine == Engine::Pipe ? PipeCfg<float>::TILE : TileCfg<float>::TILE;
+        per = p.engine == Engine::Stream ? p.geom.swath_items : p.tile_items;
     }
     *num_swaths = n;
     if (!d_coords) return 0;
@@ -787,9 +864,9 @@ int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out
         if (rc) return rc;
         if (p.engine == Engine::Pipe) {
             out[0] = p.num_blocks;
-            out[1] = PipeCfg<T>::THREADS;
-            out[2] = PipeCfg<T>::TILE;
-            out[3] = (int)pipe_smem_bytes<T>();
+            out[1] = p.pipe_cfg ? PipeCfgB<T>::THREADS : PipeCfgA<T>::THREADS;
+            out[2] = p.tile_items;
+            out[3] = (int)(p.pipe_cfg ? pipe_smem_bytes<PipeCfgB<T>>() : pipe_smem_bytes<PipeCfgA<T>>());
             out[4] = pipe_search() ? 1 : 2;
         } else if (p.engine == Engine::Stream) {
             out[0] = p.geom.num_swaths;
@@ -840,6 +917,11 @@ int mspmv_set_option(const char* name, int value)
     }
     if (!std::strcmp(name, "pipe_blocks_per_sm")) {
         g_pipe_blocks_per_sm = value < 0 ? -1 : value;
+        return 0;
+    }
+    if (!std::strcmp(name, "pipe_config")) {
+        if (value > 2) return 1;
+        g_pipe_config = value < 0 ? -1 : value;
         return 0;
     }
     if (!std::strcmp(name, "pipe_smem_kb")) {

@@ -5,31 +5,33 @@
 // What one call does (the reference needs three launches: search, spmv, fix-up --
 // dispatch_spmv_orig.cuh:665-745):
 //   * grid = min(tiles, SMs x resident blocks); block b owns tiles [b*T/G, (b+1)*T/G).
-//   * warp 4 of every block is the PRODUCER.  It walks the block's piece of the merge path itself:
-//     the run's start coordinate by a warp-cooperative 32-ary MergePathSearch over the whole matrix
-//     (thread_search.cuh:53-84, same unique coordinate), every further tile boundary by a 32-ary
-//     search bounded to the <= TILE rows the tile can span (2-3 dependent L2 trips, off the
-//     consumers' critical path) -- this replaces DeviceSpmvSearchKernel
-//     (dispatch_spmv_orig.cuh:104-143).  For each tile it issues three cp.async.bulk copies (TMA,
-//     SASS UBLKCP): the tile's values, column indices and row-offset slice, into one stage of a
-//     shared-memory ring, completing on that stage's `full` mbarrier.
-//   * warps 0-3 are the CONSUMERS (all of them compute; there is no gather/reduce specialisation).
+//   * the last warp of every block is the PRODUCER.  It walks the block's piece of the merge path
+//     itself: the run's start coordinate by a warp-cooperative 32-ary MergePathSearch over the whole
+//     matrix (thread_search.cuh:53-84, same unique coordinate), every further tile boundary by a
+//     bounded search whose first probe is a 32-row window placed where the previous tile's row count
+//     predicts the boundary (one L2 trip for regular matrices, off the consumers' critical path) --
+//     this replaces DeviceSpmvSearchKernel (dispatch_spmv_orig.cuh:104-143).  For each tile it issues
+//     cp.async.bulk copies (TMA, SASS UBLKCP) into two shared-memory rings, each slot with a
+//     full / empty mbarrier pair: the column indices (needed only until the tile's gathers are
+//     issued) and the values + row-offset slice (needed until the tile's rows are stored).
+//   * the other warps are the CONSUMERS (all of them compute; no gather/reduce specialisation).
 //     Per tile, with nnzs nonzeros and nrows row ends:
+//       G   every thread owns IPT consecutive nonzero SLOTS: reads its column indices (shared
+//           memory) and issues the x[col] gathers (LDG, cache-hinted) -- with GATHER_AHEAD one tile
+//           ahead of the walk, so the gathers fly while the previous tile is walked and stored;
 //       P1  row owners (thread r <-> row r of the tile) set bit (row_end[r] - y0) of a bitmap: a
-//           row boundary lies in front of that nonzero slot (slot nnzs = boundary at the tile's end);
-//       W   every thread owns IPT consecutive nonzero SLOTS: reads its flag bits, its column
-//           indices (shared memory), gathers x[col] (LDG, cache-hinted), then walks its slots:
-//           running = fma(value, x, running); at a flagged slot the finished segment sum is parked
-//           IN PLACE (the slot's own value is already in a register) and the sum restarts
-//           (the merge walk of agent_spmv_orig.cuh:557-578 without per-item row bookkeeping);
+//           row boundary lies in front of that slot (slot nnzs = boundary at the tile's end);
+//       W   walk my slots: running = fma(value, x, running); at a flagged slot the finished
+//           segment sum is parked IN PLACE (the slot's own value is already in a register) and the
+//           sum restarts (the merge walk of agent_spmv_orig.cuh:557-578 without per-item row
+//           bookkeeping);
 //       S   one warp-shuffle segmented scan of (had a boundary, tail sum) per thread
 //           (ReduceByKeyOp, thread_operators.cuh:278-302) gives every thread the partial that
 //           precedes it -- added to its first parked segment -- and the tile's carry-out, which
 //           stays in registers for the block's next tile;
 //       Y   row owners read their row's parked sum and store y, coalesced (empty rows get 0).
-//     P1 of tile i+1 runs before the barrier that ends S of tile i, so a tile costs two
-//     128-thread named barriers.  The stage is handed back to the producer through its `empty`
-//     mbarrier.
+//     P1 of tile i+1 runs before the barrier that ends S of tile i, so a tile costs two named
+//     barriers among the consumers.
 //   * a block's last carry-out (row, partial) goes to global memory; the last block to finish
 //     (ticket) folds the G carries into y in carry order -- the serial loop of
 //     cpu_spmv.cpp:348-352, guard row < num_rows -- replacing DeviceSegmentFixupKernel
@@ -43,70 +45,62 @@
 
 namespace mspmv {
 
-#ifndef MSPMV_PIPE_IPT
-#define MSPMV_PIPE_IPT (sizeof(T) == 8 ? 9 : 13)
-#endif
-#ifndef MSPMV_PIPE_STAGES
-#define MSPMV_PIPE_STAGES 2   // slots of the value / row-offset ring
-#endif
-#ifndef MSPMV_PIPE_CSTAGES
-#define MSPMV_PIPE_CSTAGES 2  // slots of the column-index ring
-#endif
-#ifndef MSPMV_PIPE_CONSUMER_WARPS
-#define MSPMV_PIPE_CONSUMER_WARPS 4
-#endif
-
-template <typename T>
+// Compile-time shape of one kernel instantiation.
+//   IPT     nonzero slots per consumer thread (odd: conflict-free strided shared-memory reads)
+//   VST     slots of the value / row-offset ring      CST   slots of the column-index ring
+//   AHEAD   1: gathers of tile i+1 are issued before tile i is walked (software pipelining)
+//   NW      consumer warps per block
+template <typename T, int IPT_, int VST_, int CST_, int AHEAD_, int NW_ = 4>
 struct PipeCfg {
-    static constexpr int NW = MSPMV_PIPE_CONSUMER_WARPS;  // consumer warps
+    using value_type = T;
+    static constexpr int NW = NW_;
     static constexpr int CONSUMERS = NW * 32;
-    static constexpr int THREADS = CONSUMERS + 32;         // + the producer warp
-    static constexpr int IPT = MSPMV_PIPE_IPT;             // nonzero slots per consumer thread (odd: conflict-free strided LDS)
-    static constexpr int TILE = CONSUMERS * IPT;           // merge items per tile
-    static constexpr int STAGES = MSPMV_PIPE_STAGES;
-    static constexpr int CSTAGES = MSPMV_PIPE_CSTAGES;
-    static constexpr int BW = TILE / 32 + 2;               // bitmap words (slot TILE is never flagged; +1 for the funnel shift)
-    static constexpr int ROWCAP = 384;                     // row offsets staged per tile; tiles with more rows read them through L2
+    static constexpr int THREADS = CONSUMERS + 32;  // + the producer warp
+    static constexpr int IPT = IPT_;
+    static constexpr int TILE = CONSUMERS * IPT;    // merge items per tile
+    static constexpr int STAGES = VST_;
+    static constexpr int CSTAGES = CST_;
+    static constexpr bool AHEAD = AHEAD_ != 0;
+    static constexpr int BW = TILE / 32 + 2;        // bitmap words (slot TILE is never flagged; +1 for the funnel shift)
+    // row offsets staged per tile (tiles with more rows read them through L2): a third of the tile, at most 384
+    static constexpr int ROWCAP = (TILE / 3 < 384 ? ((TILE / 3 + 7) & ~7) : 384);
     static constexpr int GV = 16 / (int)sizeof(T);
-    static constexpr int LOCAL_SPAN = 32768;               // see spmv_tile.cuh: L1 policy of the gathers
+    static constexpr int LOCAL_SPAN = 32768;        // see spmv_tile.cuh: L1 policy of the gathers
     static_assert(IPT >= 2 && IPT < 32 && BW <= CONSUMERS, "bitmap layout");
+    // the row offsets of tile i+1 are read (P1) while tile i still owns its slot: two value slots at least
+    static_assert(VST_ >= 2 && CST_ >= 1, "rings");
 };
 
-// Two rings, because the two halves of a tile are needed at different times: the column indices
-// only until the tile's gathers have been issued (one tile AHEAD of the walk), the values and row
-// offsets until its rows have been stored.
-template <typename T>
+template <class C>
 struct alignas(128) PipeStage {
-    using C = PipeCfg<T>;
-    T val[C::TILE + 2 * C::GV];  // staged values; a flagged slot later holds its parked segment sum
+    typename C::value_type val[C::TILE + 2 * C::GV];  // staged values; a flagged slot later holds its parked segment sum
     int row[C::ROWCAP + 8];
 };
-template <typename T>
+template <class C>
 struct alignas(128) PipeColStage {
-    int col[PipeCfg<T>::TILE + 8];
+    int col[C::TILE + 8];
 };
 
-template <typename T>
+template <class C>
 struct alignas(128) PipeCtl {
-    using C = PipeCfg<T>;
-    uint64_t full[C::STAGES];    // values + row offsets of a tile have landed
+    uint64_t full[C::STAGES];     // values + row offsets of a tile have landed
     uint64_t empty[C::STAGES];
     uint64_t full_c[C::CSTAGES];  // column indices of a tile have landed
     uint64_t empty_c[C::CSTAGES];
-    int4 coord[C::CSTAGES];      // (x0, y0, x1, y1) of the tile in the column slot (read once, kept in registers)
+    int4 coord[C::CSTAGES];       // (x0, y0, x1, y1) of the tile in the column slot (read once, kept in registers)
     uint32_t bits[2][C::BW];
-    Seg<T> warp[C::NW];
+    Seg<typename C::value_type> warp[C::NW];
     int last;
 };
 
-template <typename T>
+template <class C>
 constexpr size_t pipe_smem_bytes()
 {
-    return sizeof(PipeCtl<T>) + sizeof(PipeStage<T>) * PipeCfg<T>::STAGES +
-           sizeof(PipeColStage<T>) * PipeCfg<T>::CSTAGES;
+    return sizeof(PipeCtl<C>) + sizeof(PipeStage<C>) * C::STAGES + sizeof(PipeColStage<C>) * C::CSTAGES;
 }
 
-// 32-ary warp search for the coordinate on diagonal `diag`, x known to lie in [lo, hi].
+// 32-ary warp search for the coordinate on diagonal `diag`, x known to lie in [lo, hi]: the smallest
+// x with x == hi or row_end[x] > diag - x - 1 (thread_search.cuh:53-84; ties consume the row end first).
 __device__ __forceinline__ int2 warp_merge_path_search_bounded(int diag, const int* __restrict__ row_end_offsets,
                                                                int num_rows, int lo, int hi, int lane)
 {
@@ -125,22 +119,44 @@ __device__ __forceinline__ int2 warp_merge_path_search_bounded(int diag, const i
     return make_int2(min(lo, num_rows), diag - lo);
 }
 
-template <typename T, bool AXPBY, bool SEARCH>
-__global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
-    const T* __restrict__ values, const int* __restrict__ row_offsets,
-    const int* __restrict__ column_indices, const T* __restrict__ x, T* __restrict__ y,
+// The same search, first probing the 32 consecutive rows around lo + guess (the previous tile's row
+// count): regular matrices resolve in that one round; the rest falls through to the 32-ary search
+// over what the window excluded.
+__device__ __forceinline__ int2 warp_merge_path_search_window(int diag, const int* __restrict__ row_end_offsets,
+                                                              int num_rows, int lo, int hi, int guess, int lane)
+{
+    if (hi - lo > 32) {
+        int w0 = lo + guess - 15;  // window [w0, w0 + 32) inside [lo, hi)
+        w0 = max(lo, min(w0, hi - 32));
+        const int pivot = w0 + lane;
+        const bool go_up = __ldg(row_end_offsets + pivot) <= diag - pivot - 1;
+        const unsigned up = __ballot_sync(kFull, go_up);  // monotone: a prefix of the lanes
+        const int n_up = __popc(up);
+        if (n_up == 0) hi = w0;
+        else if (n_up == 32) lo = w0 + 32;
+        else lo = hi = w0 + n_up;
+    }
+    return warp_merge_path_search_bounded(diag, row_end_offsets, num_rows, lo, hi, lane);
+}
+
+template <class C, bool AXPBY, bool SEARCH>
+__global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
+    const typename C::value_type* __restrict__ values, const int* __restrict__ row_offsets,
+    const int* __restrict__ column_indices, const typename C::value_type* __restrict__ x,
+    typename C::value_type* __restrict__ y,
     const int2* __restrict__ coords_in,  // !SEARCH: tile coordinates from tile_search_kernel
     int2* __restrict__ coords_out,       // optional export of the coordinates the producer found
-    int* __restrict__ carry_rows, T* __restrict__ carry_vals, unsigned int* __restrict__ ticket, T alpha, T beta,
-    int num_rows, int num_nonzeros, int num_tiles, int shift_v, int shift_c, int shift_r)
+    int* __restrict__ carry_rows, typename C::value_type* __restrict__ carry_vals, unsigned int* __restrict__ ticket,
+    typename C::value_type alpha, typename C::value_type beta, int num_rows, int num_nonzeros, int num_tiles,
+    int shift_v, int shift_c, int shift_r)
 {
-    using C = PipeCfg<T>;
+    using T = typename C::value_type;
     constexpr int IPT = C::IPT, NW = C::NW, STAGES = C::STAGES, CSTAGES = C::CSTAGES, GV = C::GV;
     MSPMV_DYNAMIC_SHARED(smem_raw);
-    PipeCtl<T>& ctl = *reinterpret_cast<PipeCtl<T>*>(smem_raw);
-    PipeStage<T>* stages = reinterpret_cast<PipeStage<T>*>(smem_raw + sizeof(PipeCtl<T>));
-    PipeColStage<T>* cstages =
-        reinterpret_cast<PipeColStage<T>*>(smem_raw + sizeof(PipeCtl<T>) + sizeof(PipeStage<T>) * STAGES);
+    PipeCtl<C>& ctl = *reinterpret_cast<PipeCtl<C>*>(smem_raw);
+    PipeStage<C>* stages = reinterpret_cast<PipeStage<C>*>(smem_raw + sizeof(PipeCtl<C>));
+    PipeColStage<C>* cstages =
+        reinterpret_cast<PipeColStage<C>*>(smem_raw + sizeof(PipeCtl<C>) + sizeof(PipeStage<C>) * STAGES);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -170,29 +186,29 @@ __global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
         const uint64_t policy = l2_policy_evict_first();
         const int* row_end = row_offsets + 1;  // device_spmv.cuh:148
         const int64_t total = (int64_t)num_rows + num_nonzeros;
+        // end coordinate of tile k of the run, given its start coordinate
+        auto next_coord = [&](int k, const int2 c, int guess) -> int2 {
+            if (!SEARCH) return __ldg(coords_in + t0 + k + 1);
+            const int64_t d64 = (int64_t)(t0 + k + 1) * C::TILE;
+            const int d1 = (int)(d64 < total ? d64 : total);
+            // the path is monotone: x1 in [x0, x0 + (d1 - d0)] = [x0, d1 - y0]
+            return warp_merge_path_search_window(d1, row_end, num_rows, max(c.x, d1 - num_nonzeros),
+                                                 min(d1 - c.y, num_rows), guess, lane);
+        };
         int2 c0;
         if (SEARCH)
             c0 = warp_merge_path_search_global((int64_t)t0 * C::TILE, row_end, num_rows, num_nonzeros, lane);
         else
             c0 = __ldg(coords_in + t0);
+        int2 c1 = next_coord(0, c0, 0);
         for (int i = 0; i < n; ++i) {
             const int s = i % STAGES, sc = i % CSTAGES;
-            int2 c1;
-            if (SEARCH) {
-                const int64_t d64 = (int64_t)(t0 + i + 1) * C::TILE;
-                const int d1 = (int)(d64 < total ? d64 : total);
-                // the path is monotone: x1 in [x0, x0 + (d1 - d0)] = [x0, d1 - y0]
-                c1 = warp_merge_path_search_bounded(d1, row_end, num_rows, max(c0.x, d1 - num_nonzeros),
-                                                    min(d1 - c0.y, num_rows), lane);
-            } else {
-                c1 = __ldg(coords_in + t0 + i + 1);
-            }
             if (coords_out != nullptr && lane == 0) {
                 coords_out[t0 + i] = c0;
                 if (t0 + i + 1 == num_tiles) coords_out[num_tiles] = c1;
             }
             const int x0 = c0.x, y0 = c0.y, nrows = c1.x - c0.x, nnzs = c1.y - c0.y;
-            // column indices first: the consumers gather for this tile one tile ahead of its walk
+            // column indices first: the consumers need them earliest
             if (i >= CSTAGES) mbar_wait(&ctl.empty_c[sc], (uint32_t)((i / CSTAGES) - 1) & 1u);
             const int base_c = (y0 + shift_c) & ~3;
             uint32_t b = stage_superset<int>(column_indices, shift_c, y0, y0 + nnzs, num_nonzeros, cstages[sc].col,
@@ -203,8 +219,11 @@ __global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
                 if (b) mbar_arrive_expect_tx(&ctl.full_c[sc], b);
                 else mbar_arrive(&ctl.full_c[sc]);
             }
+            // the next tile's end coordinate, searched while the value slot is still busy
+            int2 c2 = c1;
+            if (i + 1 < n) c2 = next_coord(i + 1, c1, nrows);
             if (i >= STAGES) mbar_wait(&ctl.empty[s], (uint32_t)((i / STAGES) - 1) & 1u);
-            PipeStage<T>& st = stages[s];
+            PipeStage<C>& st = stages[s];
             const int base_v = (y0 + shift_v) & ~(GV - 1);
             const int jr0 = x0 + 1;  // row_end_offsets[x0 + r] == row_offsets[jr0 + r]
             const int base_r = (jr0 + shift_r) & ~3;
@@ -219,13 +238,14 @@ __global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
                 else mbar_arrive(&ctl.full[s]);
             }
             c0 = c1;
+            c1 = c2;
         }
         return;
     }
 
     // =============================== consumer warps ===============================================
     // P1: row owners flag the slot in front of which their row ends
-    auto mark_rows = [&](const int4 c, const PipeStage<T>& st, uint32_t* bits) {
+    auto mark_rows = [&](const int4 c, const PipeStage<C>& st, uint32_t* bits) {
         const int nrows = c.z - c.x, jr0 = c.x + 1;
         const int off_r = (jr0 + shift_r) & 3;
         for (int r = tid; r < nrows; r += C::CONSUMERS) {
@@ -238,8 +258,8 @@ __global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
     const uint64_t keep = l2_policy_evict_last();  // x is the only reused data: keep it in L2
     const int base = tid * IPT;  // my first slot
 
-    // G: read my column indices of tile k and issue the x gathers; the values come back while the
-    // PREVIOUS tile is walked, scanned and stored (the loads are only consumed one step later).
+    // G: read my column indices of tile k and issue the x gathers (consumed by the walk: with
+    // GATHER_AHEAD one step later, the loads fly while the previous tile is walked and stored).
     auto gather = [&](int k, const int4 c, T(&xo)[IPT]) {
         const int sc = k % CSTAGES;
         const int nnzs = c.w - c.y;
@@ -274,21 +294,25 @@ __global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
     T xa[IPT], xb[IPT];
     mbar_wait(&ctl.full_c[0], 0);
     cur = ctl.coord[0];
-    gather(0, cur, xa);
+    if (C::AHEAD) gather(0, cur, xa);
     mbar_wait(&ctl.full[0], 0);
     mark_rows(cur, stages[0], ctl.bits[0]);
     nxt = cur;
     named_bar_sync(2, C::CONSUMERS);
 
-    // one tile: xc = the x values gathered for it one step ago, xn = where the next tile's go
+    // one tile: xc = its x values (AHEAD: gathered one step ago), xn = where the next tile's go
     auto step = [&](int i, T(&xc)[IPT], T(&xn)[IPT]) {
         const int s = i % STAGES, bsel = i & 1;
-        PipeStage<T>& st = stages[s];
-        if (i + 1 < n) {
-            const int sc1 = (i + 1) % CSTAGES;
-            mbar_wait(&ctl.full_c[sc1], (uint32_t)((i + 1) / CSTAGES) & 1u);
-            nxt = ctl.coord[sc1];
-            gather(i + 1, nxt, xn);
+        PipeStage<C>& st = stages[s];
+        if (C::AHEAD) {
+            if (i + 1 < n) {
+                const int sc1 = (i + 1) % CSTAGES;
+                mbar_wait(&ctl.full_c[sc1], (uint32_t)((i + 1) / CSTAGES) & 1u);
+                nxt = ctl.coord[sc1];
+                gather(i + 1, nxt, xn);
+            }
+        } else {
+            gather(i, cur, xc);
         }
         const int x0 = cur.x, y0 = cur.y, nrows = cur.z - cur.x, nnzs = cur.w - cur.y;
         const int off_v = (y0 + shift_v) & (GV - 1);
@@ -321,6 +345,11 @@ __global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
 
         // ---- P1 of the next tile, then the barrier that publishes the parked sums -----------------
         if (i + 1 < n) {
+            if (!C::AHEAD) {
+                const int sc1 = (i + 1) % CSTAGES;
+                mbar_wait(&ctl.full_c[sc1], (uint32_t)((i + 1) / CSTAGES) & 1u);
+                nxt = ctl.coord[sc1];
+            }
             const int s1 = (i + 1) % STAGES;
             mbar_wait(&ctl.full[s1], (uint32_t)((i + 1) / STAGES) & 1u);
             mark_rows(nxt, stages[s1], ctl.bits[bsel ^ 1]);
@@ -350,9 +379,13 @@ __global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
         if (lane == 0) mbar_arrive(&ctl.empty[s]);
         cur = nxt;
     };
-    for (int i = 0; i < n; i += 2) {  // ping-pong register sets: no copy waits for the gathers in flight
-        step(i, xa, xb);
-        if (i + 1 < n) step(i + 1, xb, xa);
+    if (C::AHEAD) {
+        for (int i = 0; i < n; i += 2) {  // ping-pong register sets: no copy waits for the gathers in flight
+            step(i, xa, xb);
+            if (i + 1 < n) step(i + 1, xb, xa);
+        }
+    } else {
+        for (int i = 0; i < n; ++i) step(i, xa, xa);
     }
 
     // ---- the run's carry-out; the last block to finish folds all of them (cpu_spmv.cpp:348-352) ---
@@ -370,8 +403,8 @@ __global__ __launch_bounds__(PipeCfg<T>::THREADS) void spmv_pipe_kernel(
     Seg<T> run;  // the run of equal rows that touches the end of the previous chunk
     run.val = T(0);
     run.ended = 0;
-    for (int base = 0; base < G; base += C::CONSUMERS) {
-        const int i = base + tid;
+    for (int cb = 0; cb < G; cb += C::CONSUMERS) {
+        const int i = cb + tid;
         const int row = i < G ? carry_rows[i] : INT_MAX;
         const int prev_row = (i > 0 && i < G) ? carry_rows[i - 1] : -1;
         const int next_row = i + 1 < G ? carry_rows[i + 1] : INT_MAX;

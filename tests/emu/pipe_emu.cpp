@@ -20,11 +20,18 @@ int shift_of(const void* p)
     return (int)((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
 }
 
+// kernel shape under test: <IPT fp64, IPT fp32, value-ring slots, column-ring slots, gather-ahead, consumer warps>
+#ifndef EMU_PIPE_CFG
+#define EMU_PIPE_CFG 9, 13, 2, 2, 0, 4
+#endif
+template <typename T, int I64, int I32, int VST, int CST, int AHEAD, int NW>
+using CfgSel = PipeCfg<T, (sizeof(T) == 8 ? I64 : I32), VST, CST, AHEAD, NW>;
+
 template <typename T, bool AXPBY>
 int run(const T* values, const int* row_offsets, const int* col, const T* x, T* y, int num_rows, int num_nonzeros,
         T alpha, T beta, int max_blocks, int search, int* coords_out, int* stats)
 {
-    using C = PipeCfg<T>;
+    using C = CfgSel<T, EMU_PIPE_CFG>;
     if (num_rows <= 0) return 0;
     const int64_t merge_items = (int64_t)num_rows + num_nonzeros;
     const int num_tiles = (int)((merge_items + C::TILE - 1) / C::TILE);
@@ -53,11 +60,11 @@ int run(const T* values, const int* row_offsets, const int* col, const T* x, T* 
     int2* cout = reinterpret_cast<int2*>(coords_out);
     emu::launch((unsigned)num_blocks, (unsigned)C::THREADS, [&] {
         if (search)
-            spmv_pipe_kernel<T, AXPBY, true>(values, row_offsets, col, x, y, nullptr, cout, cr_buf.data(), cv_buf.data(),
+            spmv_pipe_kernel<C, AXPBY, true>(values, row_offsets, col, x, y, nullptr, cout, cr_buf.data(), cv_buf.data(),
                                              &ticket, alpha, beta, num_rows, num_nonzeros, num_tiles,
                                              shift_of<T>(values), shift_of<int>(col), shift_of<int>(row_offsets));
         else
-            spmv_pipe_kernel<T, AXPBY, false>(values, row_offsets, col, x, y, coords_buf.data(), cout, cr_buf.data(),
+            spmv_pipe_kernel<C, AXPBY, false>(values, row_offsets, col, x, y, coords_buf.data(), cout, cr_buf.data(),
                                               cv_buf.data(), &ticket, alpha, beta, num_rows, num_nonzeros, num_tiles,
                                               shift_of<T>(values), shift_of<int>(col), shift_of<int>(row_offsets));
     });

@@ -22,10 +22,12 @@ from conftest import GOLDEN, ROOT, random_csr
 
 EMU = os.path.join(ROOT, "tests", "emu")
 CSRC = os.path.join(ROOT, "merge-spmv_b200", "csrc")
-VARIANTS = {
+VARIANTS = {  # <IPT fp64, IPT fp32, value-ring slots, column-ring slots, gather-ahead, consumer warps>
     "shipped": [],
-    "stages3_ipt_7_11": ["-DMSPMV_PIPE_STAGES=3", "-DMSPMV_PIPE_IPT=(sizeof(T)==8?7:11)"],
-    "ipt_5_5": ["-DMSPMV_PIPE_IPT=5"],
+    "ahead_2_2": ["-DEMU_PIPE_CFG=9,13,2,2,1,4"],
+    "ahead_v2_c1_ipt_7_11": ["-DEMU_PIPE_CFG=7,11,2,1,1,4"],
+    "v3_c1_ipt_5_5": ["-DEMU_PIPE_CFG=5,5,3,1,0,4"],
+    "ahead_nw2_v2_c3": ["-DEMU_PIPE_CFG=9,7,2,3,1,2"],
 }
 
 
@@ -76,7 +78,7 @@ class PipeEmu:
         xx = np.ascontiguousarray(x, dtype=dt)
         y = np.full(rows, np.nan, dtype=dt) if y_in is None else np.array(y_in, dtype=dt)
         stats = np.zeros(4, np.int32)
-        tile = 128 * self.ipt(dt)
+        tile = self.tile(dt)
         ntiles = max((rows + nnz + tile - 1) // tile, 1)
         coords = np.full((ntiles + 1, 2), -7, np.int32)
         fn = getattr(self.lib, "emu_pipe_" + ("f64" if dt == np.float64 else "f32"))
@@ -100,13 +102,15 @@ class PipeEmu:
             y = np.zeros(1, np.float64)
             self.lib.emu_pipe_f64(one.ctypes.data, ro.ctypes.data, z.ctypes.data, one.ctypes.data, y.ctypes.data, 1, 1,
                                   1.0, 0.0, 0, 1, 1, None, stats.ctypes.data)
-            t64 = int(stats[1]) // 128
+            t64 = int(stats[1])
             one32 = np.ones(1, np.float32)
             y32 = np.zeros(1, np.float32)
             self.lib.emu_pipe_f32(one32.ctypes.data, ro.ctypes.data, z.ctypes.data, one32.ctypes.data, y32.ctypes.data,
                                   1, 1, 1.0, 0.0, 0, 1, 1, None, stats.ctypes.data)
-            self._ipt = {np.dtype(np.float64): t64, np.dtype(np.float32): int(stats[1]) // 128}
+            self._ipt = {np.dtype(np.float64): t64, np.dtype(np.float32): int(stats[1])}
         return self._ipt[np.dtype(dt)]
+
+    tile = ipt  # merge items per tile of the build under test
 
     def search(self, ro, diags):
         ro = np.ascontiguousarray(ro, np.int32)
@@ -166,7 +170,7 @@ def test_pipe_random_structures_vs_oracle(emu, orc, dt):
             y = emu.csrmv(ro, col, np.ones(nnz, dt), np.ones(cols, dt), blocks=blocks, want_coords=True)
             assert np.array_equal(y, np.diff(ro).astype(dt)), (rows, cols, blocks, "exact-integer inputs must be bit-exact")
             # the coordinates the producer warp found in-kernel == the reference's MergePathSearch
-            assert np.array_equal(emu.coords, oracle_tile_coords(orc, ro, 128 * emu.ipt(dt))), (rows, cols, blocks)
+            assert np.array_equal(emu.coords, oracle_tile_coords(orc, ro, emu.tile(dt))), (rows, cols, blocks)
         val = (0.5 + rng.random(nnz)).astype(dt)
         x = (0.5 + rng.random(cols)).astype(dt)
         want = orc.merge_csrmv(ro, col, val, x, num_threads=8)
@@ -242,7 +246,7 @@ def test_pipe_many_blocks_fold(emu0, orc):
     """More blocks than one fold chunk (128), long rows spanning many blocks: the last block's chunked
     segmented scan over the per-block carries, with runs crossing chunk boundaries."""
     rng = np.random.default_rng(4)
-    tile = 128 * emu0.ipt(np.float64)
+    tile = emu0.tile(np.float64)
     lens = np.concatenate([rng.integers(0, 4, 300), [tile * 150 + 17], rng.integers(0, 4, 50), [tile * 140 + 3],
                            rng.integers(0, 30, 2000)]).astype(np.int64)
     cols = int(lens.max())
@@ -313,7 +317,7 @@ def test_pipe_tile_boundary_cases(emu0, orc, dt):
     across a boundary, tiles made only of empty rows (more row ends than ROWCAP), a row spanning
     several tiles, trailing empty rows, degenerate sizes; aligned and misaligned bases; bit-exact
     against SpmvGold on small-integer inputs."""
-    tile = 128 * emu0.ipt(dt)
+    tile = emu0.tile(dt)
     cases = [
         ([tile - 1] * 3, 2000), ([tile] * 3, 2000), ([tile - 2, 0] * 3, 2000), ([0] * (tile * 2), 5),
         ([0] * (tile * 2 + 1), 5), ([1] * (tile // 2 * 3), 7), ([0] * 500 + [1900] + [0] * 700, 2000),

@@ -22,9 +22,9 @@ if [ "${SKIP_TESTS:-0}" != 1 ]; then
     timeout 1200 $PY -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee -a "$LOG"
 fi
 echo "== shipped build: tile engine (round 1) vs pipe engine" | tee -a "$LOG"
-lib shipped "engine=tile;engine=pipe;engine=pipe,pipe_search=0"
+lib shipped "engine=tile;engine=pipe;engine=pipe,pipe_search=0;engine=pipe,pipe_smem_kb=192"
 echo "== pipe: compile-time variants" | tee -a "$LOG"
-for B in ${VARIANTS:-p_ipt7_11 p_ipt11_15 p_ipt5_9 p_st3 p_st3_ipt7_11 p_st3_ipt5_9 p_nw8 p_nw8_ipt5_7}; do
+for B in ${VARIANTS:-p_base p_c1 p_ah p_ah_c1 p_ipt11 p_ipt11_c1 p_ah_ipt7_c1 p_nw8_c1 p_nw2 p_nw2_c1 p_nw2_ah_c1 p_nw1 p_nw1_ipt15 p_nw2_ipt13}; do
     [ -f $V/libmergespmv_$B.so ] && lib $B "engine=pipe" MSPMV_LIB=$V/libmergespmv_$B.so
 done
 echo "== pipe: shared-memory budget per SM (rest is L1) / resident blocks" | tee -a "$LOG"
