@@ -237,13 +237,12 @@ def main():
     ap.add_argument("--values", default="random", choices=["ones", "random"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--engine", default=None, choices=[None, "stream", "tile", "auto"])
+    ap.add_argument("--engine", default=None, choices=[None, "pipe", "auto"])
     ap.add_argument("--cols", type=int, default=None, help="override the column count (x length) of the workload")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay each step (3 kernels, plus the collective and carry fold at N>1) as one CUDA graph; auto = on")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
-                    help="mspmv_set_option before the run (opt-in kernel variants, e.g. tile_variant=3, "
-                         "small_fused_tiles=4096); recorded in config.options")
+                    help="mspmv_set_option before the run (e.g. pipe_config=2, pipe_search=0); recorded in config.options")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
                     help="N>1: how the carries travel -- nccl: one all_gather + fold kernel (default); p2p: one kernel "
                          "per rank storing into the peers' symmetric memory over NVLink (csrc/carry_exchange.cuh)")
@@ -370,8 +369,7 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(f"{name}@{world}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": ("spmv_stream_kernel" if (args.engine or "tile") == "stream" else
-                           "spmv_tile3_kernel" if options.get("tile_variant") == 3 else "spmv_tile_kernel"),
+                "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_pipe_kernel",
                 "algorithmic_bytes_per_launch": shard_bytes,
                 "frac_of_nominal_8000_gbs": achieved / 8000.0,  # BASELINE.md section 2 also asks for the nominal figure
                 "note": "duration = whole step (search + tile + carry fix-up kernels; the tile kernel is 94.7% of it, profiles/launches_r01.csv), CUDA events"}
@@ -496,7 +494,7 @@ def main():
                            kind, "stratified-uniform over all columns, sorted, distinct"),
                        "parallelism": f"merge-path shards x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
-                       "engine": args.engine or "tile", "cuda_graph": use_graph, "gather_y": gather_y, "options": options,
+                       "engine": "pipe", "cuda_graph": use_graph, "gather_y": gather_y, "options": options,
                        "carry_exchange": (args.exchange if world > 1 else None)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),

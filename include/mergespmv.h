@@ -178,28 +178,29 @@ int mspmv_version(void); /* major*100 + minor */
 int mspmv_ptx_version(int* ptx_version);
 /* Kernel launches issued by this library since load (all entry points). */
 uint64_t mspmv_launch_count(void);
-/* Launch geometry mspmv_csrmv_* uses for a shape: out[0] = swaths (threadblocks),
- * out[1] = threads per block, out[2] = merge items per tile, out[3] = dynamic smem bytes,
- * out[4] = kernels per call. */
+/* Launch geometry mspmv_csrmv_* uses for a shape (6 ints): out[0] = threadblocks (each owns a
+ * contiguous run of tiles), out[1] = threads per block, out[2] = merge items per tile,
+ * out[3] = dynamic smem bytes per block, out[4] = kernels per call (1), out[5] = tiles
+ * (equal-length diagonal swaths of the merge path). */
 int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out);
 const char* mspmv_error_string(int err);
-/* Test hook: pick the kernel engine for subsequent calls in this process: "tile" (one threadblock
- * per tile + search kernel; what "auto", the default, selects) or "stream" (persistent TMA-fed
- * swaths, kept as a test subject).  Also settable with the MSPMV_ENGINE environment variable.
- * Returns 0, or 1 for a bad name. */
+/* Kept for callers that name an engine: "auto" and "pipe" (the one engine, csrc/spmv_pipe.cuh)
+ * return 0, anything else 1. */
 int mspmv_set_engine(const char* name);
-/* Tuning options of the tile engine for subsequent calls in this process.  Returns 0, or 1 for an
- * unknown name.
- *   "small_fused_tiles"  n > 0: matrices of at most n tiles run as ONE launch (each block searches
- *                        its own merge-path coordinates, the last block to finish folds the
- *                        carries) instead of search + tile + fix-up kernels -- the small-matrix
- *                        overhead the paper names (section IV.B; dispatch_spmv_orig.cuh:674-679).
- *                        0: off (default).  -1: back to the MSPMV_SMALL_FUSED environment value.
- *   "tile_variant"       2: the shipped tile kernel (default).  3: spmv_tile3_kernel -- thread-blocked
- *                        gathers, products kept in registers (csrc/spmv_tile3.cuh); same bits.
- *                        0: chosen per call -- variant 3 when (rows + nnz) / rows is at most
- *                        "auto_v3_max_row_items" (default 0: never).  -1: back to MSPMV_TILE_VARIANT.
- *   "auto_v3_max_row_items"  the threshold of tile_variant 0. */
+/* Tuning / test options for subsequent calls in this process.  Returns 0, or 1 for an unknown name.
+ * value -1 returns an option to its environment value / default.
+ *   "pipe_search"         1 (default): the producer warp of every threadblock finds its tile
+ *                         coordinates itself -- ONE launch per CsrMV (plus a 4-byte memset node).
+ *                         0: DeviceSpmvSearchKernel's analogue runs first (dispatch_spmv_orig.cuh:689),
+ *                         two launches.  Same tiles, same bits.
+ *   "pipe_config"         0 (default): kernel shape by average row length -- B for
+ *                         (rows + nnz) / rows <= 16, else A (the analogue of the reference's
+ *                         per-type tile policies, dispatch_spmv_orig.cuh:393-441).  1: A.  2: B.
+ *   "pipe_smem_kb"        shared-memory budget per SM that sizes the grid (default A 160, B 192; the
+ *                         rest of the 228 KB stays L1 for the x gathers' misses in flight).
+ *   "pipe_blocks_per_sm"  cap on resident threadblocks per SM (0 = what the budget allows).
+ *   "pipe_export_coords"  1: the producer warps also write the coordinates they found to the start
+ *                         of the temp blob (tiles + 1 int2; the bit-exact MergePathSearch check). */
 int mspmv_set_option(const char* name, int value);
 
 #ifdef __cplusplus

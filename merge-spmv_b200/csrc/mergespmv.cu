@@ -19,9 +19,7 @@
 
 #include "../../include/mergespmv.h"
 #include "merge_common.cuh"
-#include "spmv_stream.cuh"
-#include "spmv_tile.cuh"
-#include "spmv_tile3.cuh"
+#include "merge_search.cuh"
 #include "spmv_pipe.cuh"
 #include "carry_exchange.cuh"
 
@@ -59,65 +57,6 @@ static int device_info(DeviceInfo& out)
     return 0;
 }
 
-enum class Engine { Auto, Tile, Stream, Pipe };
-
-static std::atomic<int> g_engine_override{-1};
-
-static Engine engine_from_env()
-{
-    int o = g_engine_override.load(std::memory_order_relaxed);
-    if (o >= 0) return (Engine)o;
-    static Engine e = [] {
-        const char* s = std::getenv("MSPMV_ENGINE");
-        if (s && !std::strcmp(s, "tile")) return Engine::Tile;
-        if (s && !std::strcmp(s, "stream")) return Engine::Stream;
-        if (s && !std::strcmp(s, "pipe")) return Engine::Pipe;
-        return Engine::Auto;
-    }();
-    return e;
-}
-
-#ifndef MSPMV_TILE_PREFETCH_DEFAULT
-#define MSPMV_TILE_PREFETCH_DEFAULT 0  // 0 = off (shipped); -1 = sm_count * 11
-#endif
-
-// Single-launch path for small matrices (spmv_tile_fused_kernel): used when the tile count is at
-// most this threshold.  0 = off (shipped default until it has been timed on the GPU);
-// MSPMV_SMALL_FUSED=<tiles> or mspmv_set_option("small_fused_tiles", n) turn it on.
-static std::atomic<int> g_small_fused_tiles{-1};
-static int small_fused_tiles()
-{
-    int v = g_small_fused_tiles.load(std::memory_order_relaxed);
-    if (v >= 0) return v;
-    static int env = [] {
-        const char* e = std::getenv("MSPMV_SMALL_FUSED");
-        return e ? std::atoi(e) : 0;
-    }();
-    return env > 0 ? env : 0;
-}
-
-// Tile kernel variant: 2 = tile_body (shipped), 3 = tile_body_v3 (spmv_tile3.cuh; opt-in until timed),
-// 0 = per call by average row length: variant 3 when (rows + nnz) / rows <= "auto_v3_max_row_items"
-// (short rows are where the tile kernel is instruction-bound; the threshold is 0 = never until the
-// round-2 sweep has placed it).  MSPMV_TILE_VARIANT / mspmv_set_option("tile_variant", v).
-static std::atomic<int> g_tile_variant{-1};
-static std::atomic<int> g_auto_v3_max_row_items{0};
-static int tile_variant(int num_rows, int num_nonzeros)
-{
-    int v = g_tile_variant.load(std::memory_order_relaxed);
-    if (v < 0) {
-        static int env = [] {
-            const char* e = std::getenv("MSPMV_TILE_VARIANT");
-            return e ? std::atoi(e) : 2;
-        }();
-        v = (env == 3 || env == 0) ? env : 2;
-    }
-    if (v != 0) return v;
-    const int limit = g_auto_v3_max_row_items.load(std::memory_order_relaxed);
-    const int64_t items = (int64_t)num_rows + num_nonzeros;
-    return (num_rows > 0 && items <= (int64_t)limit * num_rows) ? 3 : 2;
-}
-
 // ---- pipe engine knobs (mspmv_set_option / environment; -1 = environment / default) ----------------
 //   pipe_search        1: the producer warp finds the tile coordinates itself (one launch per CsrMV, default)
 //                      0: tile_search_kernel first (two launches)
@@ -143,12 +82,15 @@ static int pipe_blocks_per_sm_opt()
     static int env = env_int("MSPMV_PIPE_BLOCKS_PER_SM", 0);
     return env;
 }
-static int pipe_smem_kb()
+// A (gather-bound): 160 KB of shared memory, 68 KB of L1 for the gather misses in flight; B (short rows,
+// streaming-bound): 192 KB, one more resident block (profiles/sweep_r02_*.txt)
+static int pipe_smem_kb(int cfg)
 {
     int v = g_pipe_smem_kb.load(std::memory_order_relaxed);
     if (v > 0) return v;
-    static int env = env_int("MSPMV_PIPE_SMEM_KB", 160);
-    return env;
+    static int env = env_int("MSPMV_PIPE_SMEM_KB", 0);
+    if (env > 0) return env;
+    return cfg ? 192 : 160;
 }
 
 // Two instantiations of the pipe kernel per value type: A for matrices with long rows (the x gathers
@@ -156,7 +98,7 @@ static int pipe_smem_kb()
 // column-ring slots, gather-ahead, consumer warps>; overridable at build time for tuning sweeps.
 // (nvcc splits -D values at commas, hence one macro per field; PB_* default to PA_*)
 #ifndef PA_I64
-#define PA_I64 9
+#define PA_I64 11
 #endif
 #ifndef PA_I32
 #define PA_I32 13
@@ -165,7 +107,7 @@ static int pipe_smem_kb()
 #define PA_VST 2
 #endif
 #ifndef PA_CST
-#define PA_CST 2
+#define PA_CST 1
 #endif
 #ifndef PA_AHEAD
 #define PA_AHEAD 0
@@ -174,7 +116,7 @@ static int pipe_smem_kb()
 #define PA_NW 4
 #endif
 #ifndef PB_I64
-#define PB_I64 PA_I64
+#define PB_I64 9
 #endif
 #ifndef PB_I32
 #define PB_I32 PA_I32
@@ -183,7 +125,7 @@ static int pipe_smem_kb()
 #define PB_VST PA_VST
 #endif
 #ifndef PB_CST
-#define PB_CST PA_CST
+#define PB_CST 2
 #endif
 #ifndef PB_AHEAD
 #define PB_AHEAD PA_AHEAD
@@ -217,10 +159,10 @@ static int pipe_config_for(int num_rows, int num_nonzeros)
 }
 
 template <class C>
-static int pipe_blocks_per_sm()
+static int pipe_blocks_per_sm(int cfg)
 {
     const int per_block = (int)pipe_smem_bytes<C>() + 1024;  // + the per-block reservation of the driver
-    int b = pipe_smem_kb() * 1024 / per_block;
+    int b = pipe_smem_kb(cfg) * 1024 / per_block;
     const int by_threads = 2048 / C::THREADS;
     if (b > by_threads) b = by_threads;
     const int want = pipe_blocks_per_sm_opt();
@@ -232,56 +174,38 @@ static inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
 
 template <typename T>
 struct Plan {
-    Engine engine;
     int64_t merge_items;
-    int num_tiles;      // tile engine: tiles; stream engine: swaths (threadblocks)
-    int num_fix_blocks;  // tile engine: level-1 fix-up blocks
-    int num_blocks;      // pipe engine: threadblocks (each owns a contiguous run of tiles)
-    int pipe_cfg;        // pipe engine: 0 = PipeCfgA, 1 = PipeCfgB
-    int tile_items;      // merge items per tile of the chosen kernel
-    size_t off_coords, off_carry_rows, off_carry_vals, off_carry2_rows, off_carry2_vals, off_ticket, bytes;
-    StreamGeom geom;    // stream engine only
+    int num_tiles;   // equal-length diagonal swaths of the merge path
+    int num_blocks;  // threadblocks (each owns a contiguous run of tiles)
+    int pipe_cfg;    // 0 = PipeCfgA, 1 = PipeCfgB
+    int tile_items;  // merge items per tile of the chosen kernel
+    size_t off_coords, off_carry_rows, off_carry_vals, off_ticket, bytes;
 };
 
 template <typename T>
 static int make_plan(int num_rows, int num_nonzeros, Plan<T>& p)
 {
     p.merge_items = (int64_t)num_rows + num_nonzeros;
-    Engine e = engine_from_env();
     DeviceInfo di;
     int rc = device_info(di);
     if (rc) return rc;
-    if (e == Engine::Auto) e = Engine::Pipe;
-    p.engine = e;
-    p.num_blocks = 0;
-    p.pipe_cfg = 0;
-    p.tile_items = TileCfg<T>::TILE;
-    if (e == Engine::Pipe) {
-        p.pipe_cfg = pipe_config_for(num_rows, num_nonzeros);
-        p.tile_items = p.pipe_cfg ? PipeCfgB<T>::TILE : PipeCfgA<T>::TILE;
-        p.num_tiles = (int)((p.merge_items + p.tile_items - 1) / p.tile_items);
-        const int resident =
-            di.sm_count * (p.pipe_cfg ? pipe_blocks_per_sm<PipeCfgB<T>>() : pipe_blocks_per_sm<PipeCfgA<T>>());
-        p.num_blocks = p.num_tiles < resident ? p.num_tiles : resident;
-    } else if (e == Engine::Stream) {
-        p.geom = stream_geometry<T>(p.merge_items, di.sm_count);
-        p.num_tiles = p.geom.num_swaths;
-    } else {
-        p.num_tiles = (int)((p.merge_items + TileCfg<T>::TILE - 1) / TileCfg<T>::TILE);
-    }
+    p.pipe_cfg = pipe_config_for(num_rows, num_nonzeros);
+    p.tile_items = p.pipe_cfg ? PipeCfgB<T>::TILE : PipeCfgA<T>::TILE;
+    p.num_tiles = (int)((p.merge_items + p.tile_items - 1) / p.tile_items);
+    const int resident =
+        di.sm_count * (p.pipe_cfg ? pipe_blocks_per_sm<PipeCfgB<T>>(1) : pipe_blocks_per_sm<PipeCfgA<T>>(0));
+    p.num_blocks = p.num_tiles < resident ? p.num_tiles : resident;
+    // 256-byte aligned regions, like AliasTemporaries (util_device.cuh:62-103).  The tile coordinates are
+    // only written in the two-launch mode / by the debug export; the carries are one per block, but the
+    // grid depends on run-time options, so both are sized by what cannot change: sm_count * 32 blocks at most.
+    const size_t max_blocks = (size_t)(p.num_tiles < di.sm_count * 32 ? p.num_tiles : di.sm_count * 32);
     size_t off = 0;
     p.off_coords = off;
     off += align256(sizeof(int2) * (size_t)(p.num_tiles + 1));
     p.off_carry_rows = off;
-    // (the pipe engine writes one carry per block, but its grid depends on run-time options: size for tiles)
-    off += align256(sizeof(int) * (size_t)p.num_tiles);
+    off += align256(sizeof(int) * max_blocks);
     p.off_carry_vals = off;
-    off += align256(sizeof(T) * (size_t)p.num_tiles);
-    p.num_fix_blocks = (p.num_tiles + TileCfg<T>::FIX - 1) / TileCfg<T>::FIX;
-    p.off_carry2_rows = off;
-    off += align256(sizeof(int) * (size_t)p.num_fix_blocks);
-    p.off_carry2_vals = off;
-    off += align256(sizeof(T) * (size_t)p.num_fix_blocks);
+    off += align256(sizeof(T) * max_blocks);
     p.off_ticket = off;
     off += 256;
     p.bytes = off + 256;  // slack so an unaligned blob can be aligned up (util_device.cuh:68-80)
@@ -297,21 +221,6 @@ static int post_launch(const char* name, dim3 grid, dim3 block, size_t smem, cud
     MSPMV_TRY(cudaPeekAtLastError());
     if (debug_sync) MSPMV_TRY(cudaStreamSynchronize(stream));
     return 0;
-}
-
-// Tiles of L2 prefetch lookahead for the tile engine: roughly the number of blocks resident on the
-// GPU, so a tile's slice is requested one block lifetime before the block that needs it starts.
-// MSPMV_TILE_PREFETCH overrides (0 = off).
-static int tile_prefetch_ahead()
-{
-    static int ahead = [] {
-        if (const char* e = std::getenv("MSPMV_TILE_PREFETCH")) return std::atoi(e);
-        return MSPMV_TILE_PREFETCH_DEFAULT;
-    }();
-    if (ahead >= 0) return ahead;
-    DeviceInfo di;
-    if (device_info(di)) return 0;
-    return di.sm_count * 11;
 }
 
 template <class C, bool AXPBY, bool SEARCH>
@@ -330,7 +239,7 @@ static int pipe_launch_impl(const Plan<typename C::value_type>& p, int2* coords,
     if (!configured[dev & 63].load(std::memory_order_relaxed)) {
         MSPMV_TRY(cudaFuncSetAttribute(spmv_pipe_kernel<C, AXPBY, SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        int pct = (pipe_smem_kb() * 100 + 227) / 228;
+        int pct = (pipe_smem_kb(p.pipe_cfg) * 100 + 227) / 228;
         if (pct > 100) pct = 100;
         MSPMV_TRY(cudaFuncSetAttribute(spmv_pipe_kernel<C, AXPBY, SEARCH>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -355,6 +264,8 @@ static int pipe_launch_impl(const Plan<typename C::value_type>& p, int2* coords,
     return post_launch("spmv_pipe_kernel", grid, block, smem, stream, debug_sync);
 }
 
+static std::atomic<int> g_pipe_export_coords{0};  // debug: the producer warps write the coordinates they found
+
 template <typename T, bool AXPBY>
 static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int* row_offsets,
                         const int* col, const T* x, T* y, int num_rows, int num_nonzeros, T alpha,
@@ -363,111 +274,17 @@ static int csrmv_launch(const Plan<T>& p, char* temp, const T* values, const int
     int2* coords = reinterpret_cast<int2*>(temp + p.off_coords);
     int* carry_rows = reinterpret_cast<int*>(temp + p.off_carry_rows);
     T* carry_vals = reinterpret_cast<T*>(temp + p.off_carry_vals);
-    const int* row_end = row_offsets + 1;  // device_spmv.cuh:148
-
-    if (p.engine == Engine::Pipe) {
-        unsigned int* ticket = reinterpret_cast<unsigned int*>(temp + p.off_ticket);
-        auto go = [&](auto cfg, auto search) {
-            using C = decltype(cfg);
-            return pipe_launch_impl<C, AXPBY, decltype(search)::value>(p, coords, nullptr, carry_rows, carry_vals, ticket,
-                                                                       values, row_offsets, col, x, y, num_rows,
-                                                                       num_nonzeros, alpha, beta, stream, debug_sync);
-        };
-        if (p.pipe_cfg)
-            return pipe_search() ? go(PipeCfgB<T>(), std::true_type()) : go(PipeCfgB<T>(), std::false_type());
-        return pipe_search() ? go(PipeCfgA<T>(), std::true_type()) : go(PipeCfgA<T>(), std::false_type());
-    }
-    if (p.engine == Engine::Stream) {
-        int rc = stream_launch<T, AXPBY>(p.geom, values, row_offsets, col, x, y, num_rows,
-                                         num_nonzeros, coords, carry_rows, carry_vals, alpha, beta,
-                                         stream);
-        if (rc) return rc;
-        rc = post_launch("spmv_stream_kernel", dim3(p.geom.num_swaths), dim3(p.geom.threads),
-                         p.geom.smem_bytes, stream, debug_sync);
-        if (rc) return rc;
-        if (p.num_tiles > 1) {  // dispatch_spmv_orig.cuh:721
-            dim3 fgrid((p.num_tiles + 255) / 256), fblock(256);
-            carry_fixup_runs_kernel<T, AXPBY><<<fgrid, fblock, 0, stream>>>(carry_rows, carry_vals,
-                                                                           p.num_tiles, num_rows, y, alpha);
-            rc = post_launch("carry_fixup_runs_kernel", fgrid, fblock, 0, stream, debug_sync);
-            if (rc) return rc;
-        }
-        return 0;
-    }
-
-    using C = TileCfg<T>;
-    int* carry2_rows = reinterpret_cast<int*>(temp + p.off_carry2_rows);
-    T* carry2_vals = reinterpret_cast<T*>(temp + p.off_carry2_vals);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(temp + p.off_ticket);
-    const int shift_v = (int)((reinterpret_cast<uintptr_t>(values) & 15) / sizeof(T));
-    const int shift_c = (int)((reinterpret_cast<uintptr_t>(col) & 15) / sizeof(int));
-    const int shift_r = (int)((reinterpret_cast<uintptr_t>(row_offsets) & 15) / sizeof(int));
-    dim3 grid(p.num_tiles), block(C::THREADS);
-    if (p.num_tiles <= small_fused_tiles()) {
-        // one launch: every block searches its own coordinates, the last block folds the carries
-        static std::atomic<bool> fused_configured[64];  // per device; a benign race only repeats the call
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!fused_configured[dev & 63].load(std::memory_order_relaxed)) {
-            cudaFuncSetAttribute(spmv_tile_fused_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, 70);
-            fused_configured[dev & 63].store(true, std::memory_order_relaxed);
-        }
-        if (p.num_tiles > 1) MSPMV_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
-        spmv_tile_fused_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, carry_rows,
-                                                                    carry_vals, alpha, beta, num_rows, num_nonzeros,
-                                                                    shift_v, shift_c, shift_r, ticket);
-        return post_launch("spmv_tile_fused_kernel", grid, block, 0, stream, debug_sync);
-    }
-    dim3 sgrid((p.num_tiles + 1 + 127) / 128), sblock(128);
-    tile_search_kernel<<<sgrid, sblock, 0, stream>>>(row_end, num_rows, num_nonzeros, C::TILE, p.num_tiles,
-                                                     coords, ticket);
-    int rc = post_launch("tile_search_kernel", sgrid, sblock, 0, stream, debug_sync);
-    if (rc) return rc;
-    {
-        // Shared-memory carve-out: the x gathers need L1 capacity for their misses in flight
-        // (gather throughput halves once shared memory takes > ~160 KB of the 228 KB, see
-        // profiles/microbench_r01.txt), so cap what the resident blocks may claim.
-        static std::atomic<bool> configured[64];  // per device; a benign race only repeats the call
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!configured[dev & 63].load(std::memory_order_relaxed)) {
-            int pct = 70;  // ~160 KB shared, ~68 KB L1 (the driver default for this footprint; pinned so larger tiles keep it)
-            if (const char* e = std::getenv("MSPMV_TILE_CARVEOUT")) pct = std::atoi(e);
-            if (pct >= 0)
-                cudaFuncSetAttribute(spmv_tile_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            configured[dev & 63].store(true, std::memory_order_relaxed);
-        }
-    }
-    if (tile_variant(num_rows, num_nonzeros) == 3) {
-        static std::atomic<bool> v3_configured[64];  // per device; a benign race only repeats the call
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!v3_configured[dev & 63].load(std::memory_order_relaxed)) {
-            int pct = 70;
-            if (const char* e = std::getenv("MSPMV_TILE_CARVEOUT")) pct = std::atoi(e);
-            if (pct >= 0)
-                cudaFuncSetAttribute(spmv_tile3_kernel<T, AXPBY>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            v3_configured[dev & 63].store(true, std::memory_order_relaxed);
-        }
-        spmv_tile3_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
-                                                               carry_vals, alpha, beta, num_rows, num_nonzeros,
-                                                               shift_v, shift_c, shift_r, tile_prefetch_ahead());
-        rc = post_launch("spmv_tile3_kernel", grid, block, 0, stream, debug_sync);
-    } else {
-        spmv_tile_kernel<T, AXPBY><<<grid, block, 0, stream>>>(values, row_offsets, col, x, y, coords, carry_rows,
-                                                              carry_vals, alpha, beta, num_rows, num_nonzeros,
-                                                              shift_v, shift_c, shift_r, tile_prefetch_ahead());
-        rc = post_launch("spmv_tile_kernel", grid, block, 0, stream, debug_sync);
-    }
-    if (rc) return rc;
-    if (p.num_tiles > 1) {  // dispatch_spmv_orig.cuh:721
-        dim3 fgrid(p.num_fix_blocks), fblock(C::FIX);
-        carry_fixup_block_kernel<T, AXPBY><<<fgrid, fblock, 0, stream>>>(
-            carry_rows, carry_vals, p.num_tiles, num_rows, y, alpha, carry2_rows, carry2_vals, ticket);
-        rc = post_launch("carry_fixup_block_kernel", fgrid, fblock, 0, stream, debug_sync);
-        if (rc) return rc;
-    }
-    return 0;
+    auto go = [&](auto cfg, auto search) {
+        using C = decltype(cfg);
+        constexpr bool SEARCH = decltype(search)::value;
+        int2* coords_out = (SEARCH && g_pipe_export_coords.load(std::memory_order_relaxed)) ? coords : nullptr;
+        return pipe_launch_impl<C, AXPBY, SEARCH>(p, coords, coords_out, carry_rows, carry_vals, ticket, values,
+                                                  row_offsets, col, x, y, num_rows, num_nonzeros, alpha, beta, stream,
+                                                  debug_sync);
+    };
+    if (p.pipe_cfg) return pipe_search() ? go(PipeCfgB<T>(), std::true_type()) : go(PipeCfgB<T>(), std::false_type());
+    return pipe_search() ? go(PipeCfgA<T>(), std::true_type()) : go(PipeCfgA<T>(), std::false_type());
 }
 
 template <typename T, bool AXPBY>
@@ -630,13 +447,13 @@ int mspmv_csrmv_swath_coords(const int* d_row_offsets, int num_rows, int num_non
         int rc = make_plan<double>(num_rows, num_nonzeros, p);
         if (rc) return rc;
         n = p.num_tiles;
-        per = p.engine == Engine::Stream ? p.geom.swath_items : p.tile_items;
+        per = p.tile_items;
     } else {
         Plan<float> p;
         int rc = make_plan<float>(num_rows, num_nonzeros, p);
         if (rc) return rc;
         n = p.num_tiles;
-        per = p.engine == Engine::Stream ? p.geom.swath_items : p.tile_items;
+        per = p.tile_items;
     }
     *num_swaths = n;
     if (!d_coords) return 0;
@@ -848,7 +665,7 @@ int mspmv_ptx_version(int* ptx_version)
 {
     if (!ptx_version) return (int)cudaErrorInvalidValue;
     cudaFuncAttributes attr;
-    MSPMV_TRY(cudaFuncGetAttributes(&attr, spmv_tile_kernel<double, false>));
+    MSPMV_TRY(cudaFuncGetAttributes(&attr, spmv_pipe_kernel<PipeCfgA<double>, false, true>));
     *ptx_version = attr.ptxVersion * 10;
     return 0;
 }
@@ -862,25 +679,12 @@ int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out
         Plan<T> p;
         int rc = make_plan<T>(num_rows, num_nonzeros, p);
         if (rc) return rc;
-        if (p.engine == Engine::Pipe) {
-            out[0] = p.num_blocks;
-            out[1] = p.pipe_cfg ? PipeCfgB<T>::THREADS : PipeCfgA<T>::THREADS;
-            out[2] = p.tile_items;
-            out[3] = (int)(p.pipe_cfg ? pipe_smem_bytes<PipeCfgB<T>>() : pipe_smem_bytes<PipeCfgA<T>>());
-            out[4] = pipe_search() ? 1 : 2;
-        } else if (p.engine == Engine::Stream) {
-            out[0] = p.geom.num_swaths;
-            out[1] = p.geom.threads;
-            out[2] = p.geom.tile_items;
-            out[3] = (int)p.geom.smem_bytes;
-            out[4] = p.num_tiles > 1 ? 2 : 1;
-        } else {
-            out[0] = p.num_tiles;
-            out[1] = TileCfg<T>::THREADS;
-            out[2] = TileCfg<T>::TILE;
-            out[3] = 0;
-            out[4] = p.num_tiles <= small_fused_tiles() ? 1 : (p.num_tiles > 1 ? 3 : 2);
-        }
+        out[0] = p.num_blocks;
+        out[1] = p.pipe_cfg ? PipeCfgB<T>::THREADS : PipeCfgA<T>::THREADS;
+        out[2] = p.tile_items;
+        out[3] = (int)(p.pipe_cfg ? pipe_smem_bytes<PipeCfgB<T>>() : pipe_smem_bytes<PipeCfgA<T>>());
+        out[4] = pipe_search() ? 1 : 2;
+        out[5] = p.num_tiles;
         return 0;
     };
     return value_bytes == 8 ? fill(double()) : fill(float());
@@ -890,27 +694,14 @@ const char* mspmv_error_string(int err) { return cudaGetErrorString((cudaError_t
 
 int mspmv_set_engine(const char* name)
 {
+    // one engine since round 2 ("pipe", spmv_pipe.cuh); the entry point stays for callers that name it
     if (!name) return 1;
-    if (!std::strcmp(name, "auto")) g_engine_override = -1;
-    else if (!std::strcmp(name, "tile")) g_engine_override = (int)Engine::Tile;
-    else if (!std::strcmp(name, "stream")) g_engine_override = (int)Engine::Stream;
-    else if (!std::strcmp(name, "pipe")) g_engine_override = (int)Engine::Pipe;
-    else return 1;
-    return 0;
+    return (!std::strcmp(name, "auto") || !std::strcmp(name, "pipe")) ? 0 : 1;
 }
 
 int mspmv_set_option(const char* name, int value)
 {
     if (!name) return 1;
-    if (!std::strcmp(name, "small_fused_tiles")) {
-        g_small_fused_tiles = value < 0 ? -1 : value;  // -1: back to the environment / default
-        return 0;
-    }
-    if (!std::strcmp(name, "tile_variant")) {
-        if (value != -1 && value != 0 && value != 2 && value != 3) return 1;
-        g_tile_variant = value;  // -1: back to the environment / default
-        return 0;
-    }
     if (!std::strcmp(name, "pipe_search")) {
         g_pipe_search = value < 0 ? -1 : (value != 0);
         return 0;
@@ -928,8 +719,8 @@ int mspmv_set_option(const char* name, int value)
         g_pipe_smem_kb = value <= 0 ? -1 : value;
         return 0;
     }
-    if (!std::strcmp(name, "auto_v3_max_row_items")) {
-        g_auto_v3_max_row_items = value < 0 ? 0 : value;
+    if (!std::strcmp(name, "pipe_export_coords")) {
+        g_pipe_export_coords = value > 0;
         return 0;
     }
     return 1;

@@ -65,7 +65,7 @@ struct PipeCfg {
     // row offsets staged per tile (tiles with more rows read them through L2): a third of the tile, at most 384
     static constexpr int ROWCAP = (TILE / 3 < 384 ? ((TILE / 3 + 7) & ~7) : 384);
     static constexpr int GV = 16 / (int)sizeof(T);
-    static constexpr int LOCAL_SPAN = 32768;        // see spmv_tile.cuh: L1 policy of the gathers
+    static constexpr int LOCAL_SPAN = 32768;        // columns; a warp whose indices span fewer lets its gathers allocate in L1
     static_assert(IPT >= 2 && IPT < 32 && BW <= CONSUMERS, "bitmap layout");
     // the row offsets of tile i+1 are read (P1) while tile i still owns its slot: two value slots at least
     static_assert(VST_ >= 2 && CST_ >= 1, "rings");
@@ -268,7 +268,7 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         int cidx[IPT];
 #pragma unroll
         for (int j = 0; j < IPT; ++j) cidx[j] = j < n_mine ? pc[j] : -1;
-        // L1 policy per warp by column span (spmv_tile.cuh): narrow span = lines are re-used
+        // L1 policy per warp by column span (profiles/tuning_r01.txt): narrow span = lines are re-used
         int cmin = cidx[0] >= 0 ? cidx[0] : INT_MAX, cmax = cidx[0];
         if (cidx[IPT - 1] >= 0) {
             cmin = min(cmin, cidx[IPT - 1]);

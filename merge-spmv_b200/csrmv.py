@@ -170,10 +170,10 @@ def swath_coords(row_offsets, value_bytes, stream=None):
 
 
 def csrmv_config(value_bytes, num_rows, num_nonzeros):
-    out = (C.c_int * 5)()
+    out = (C.c_int * 6)()
     _lib.check(_lib.lib().mspmv_csrmv_config(value_bytes, num_rows, num_nonzeros, out))
-    return dict(swaths=out[0], threads=out[1], tile_items=out[2], smem_bytes=out[3],
-                kernels_per_call=out[4])
+    return dict(blocks=out[0], threads=out[1], tile_items=out[2], smem_bytes=out[3],
+                kernels_per_call=out[4], tiles=out[5])
 
 
 class SpmvSession:

@@ -5,8 +5,9 @@
 #define MSPMV_PTX_HEADER "ptx_emu.cuh"
 #include "simt_emu.hpp"
 
-#include "spmv_tile.cuh"  // tile_search_kernel, diagonal_search_kernel
+#include "merge_search.cuh"  // tile_search_kernel, diagonal_search_kernel
 #include "spmv_pipe.cuh"
+#include "carry_exchange.cuh"
 
 #include <vector>
 
@@ -86,6 +87,53 @@ int emu_pipe_f32(const float* v, const int* ro, const int* ci, const float* x, f
 {
     return axpby ? run<float, true>(v, ro, ci, x, y, rows, nnz, alpha, beta, max_blocks, search, coords_out, stats)
                  : run<float, false>(v, ro, ci, x, y, rows, nnz, alpha, beta, max_blocks, search, coords_out, stats);
+}
+
+// The NVLink carry exchange (carry_exchange.cuh) with `world` ranks simulated in one process: every
+// rank has its own y slice, exchange buffer and epoch counter; "peer memory" is just the other
+// rank's buffer.  Per step all ranks run the push phase, then all ranks run the fold phase (the
+// product launches both phases in one kernel; the interpreter runs one block at a time, so a
+// rank polling for a flag another rank has not written yet would never be satisfied).
+//   cuts[world+1]   first global row of every rank (rank g owns rows [cuts[g], cuts[g+1]))
+//   carry_rows[world], carries[steps][world]; y_out[steps][rows_global] = the owned rows after the fold
+int emu_exchange_f64(int world, int steps, const int* cuts, const int* carry_rows, const double* carries,
+                     double* y_out, int use_f32)
+{
+    const int rows_global = cuts[world];
+    std::vector<std::vector<uint64_t>> bufs(world, std::vector<uint64_t>(4 * (size_t)world, 0));
+    std::vector<uint64_t*> ptrs(world);
+    for (int g = 0; g < world; ++g) ptrs[g] = bufs[g].data();
+    std::vector<unsigned long long> epoch(world, 0);
+    for (int st = 0; st < steps; ++st) {
+        std::vector<std::vector<double>> yd(world);
+        std::vector<std::vector<float>> yf(world);
+        for (int g = 0; g < world; ++g) {
+            const int owned = cuts[g + 1] - cuts[g];
+            yd[g].assign(owned + 1, 0.0);
+            yf[g].assign(owned + 1, 0.f);
+            for (int i = 0; i < owned; ++i) yd[g][i] = yf[g][i] = (float)(100 * st + cuts[g] + i);  // "A*x" of the owned rows
+            yd[g][owned] = carries[(size_t)st * world + g];
+            yf[g][owned] = (float)carries[(size_t)st * world + g];
+        }
+        for (int phase = 1; phase <= 2; ++phase)
+            for (int g = 0; g < world; ++g) {
+                const int owned = cuts[g + 1] - cuts[g];
+                emu::launch(1, 32, [&] {
+                    if (use_f32)
+                        carry_exchange_kernel<float>(yf[g].data(), owned, cuts[g], owned, rows_global, carry_rows,
+                                                     ptrs.data(), g, world, &epoch[g], phase);
+                    else
+                        carry_exchange_kernel<double>(yd[g].data(), owned, cuts[g], owned, rows_global, carry_rows,
+                                                      ptrs.data(), g, world, &epoch[g], phase);
+                });
+            }
+        for (int g = 0; g < world; ++g)
+            for (int i = 0; i < cuts[g + 1] - cuts[g]; ++i)
+                y_out[(size_t)st * rows_global + cuts[g] + i] = use_f32 ? (double)yf[g][i] : yd[g][i];
+    }
+    for (int g = 0; g < world; ++g)
+        if (epoch[g] != (unsigned long long)steps) return 1;
+    return 0;
 }
 
 // thread resume order inside a block: 0 ascending, 1 descending, 2 random per pass

@@ -30,9 +30,15 @@ struct EmuBulkCopy {
     uint32_t bytes;
     uint64_t* bar;
 };
-EMU_INTERNAL inline std::vector<EmuBulkCopy>& emu_inflight()
+// in-flight copies: a plain array handled only inside EMU_INTERNAL functions, so that the interpreter's own
+// bookkeeping (touched by whichever CUDA thread issues a copy or completes a phase) is invisible to TSan
+struct EmuInflight {
+    EmuBulkCopy item[4096];
+    size_t n = 0;
+};
+EMU_INTERNAL inline EmuInflight& emu_inflight()
 {
-    static std::vector<EmuBulkCopy> v;
+    static EmuInflight v;
     return v;
 }
 // the data movement of a bulk copy, visible to the sanitizers as ordinary writes of the thread that
@@ -47,12 +53,12 @@ EMU_INTERNAL inline void emu_mbar_check_complete(uint64_t* bar)
     EmuMbar* b = emu_bar(bar);
     if (b->pending != 0 || b->tx != 0) return;
     // the phase completes: the bulk copies that signal this barrier become visible now
-    auto& fl = emu_inflight();
-    for (size_t i = 0; i < fl.size();) {
-        if (fl[i].bar == bar) {
-            emu_land_copy(fl[i].dst, fl[i].src, fl[i].bytes);
-            fl[i] = fl.back();
-            fl.pop_back();
+    EmuInflight& fl = emu_inflight();
+    for (size_t i = 0; i < fl.n;) {
+        if (fl.item[i].bar == bar) {
+            emu_land_copy(fl.item[i].dst, fl.item[i].src, fl.item[i].bytes);
+            fl.item[i] = fl.item[fl.n - 1];
+            --fl.n;
         } else {
             ++i;
         }
@@ -101,7 +107,9 @@ EMU_INTERNAL inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t
     if (((uintptr_t)dst_smem & 15) || ((uintptr_t)src_gmem & 15) || (bytes & 15) || bytes == 0)
         emu::die("cp.async.bulk: addresses must be 16-byte aligned and the size a non-zero multiple of 16");
     emu_poison_copy(dst_smem, bytes);  // not visible before the barrier phase completes
-    emu_inflight().push_back(EmuBulkCopy{dst_smem, src_gmem, bytes, bar});
+    EmuInflight& fl = emu_inflight();
+    if (fl.n == 4096) emu::die("too many bulk copies in flight");
+    fl.item[fl.n++] = EmuBulkCopy{dst_smem, src_gmem, bytes, bar};
     emu_bar(bar)->tx -= (int64_t)bytes;  // complete_tx
     emu_mbar_check_complete(bar);
 }

@@ -1,15 +1,13 @@
-// tsan_check.cpp -- the tile-engine kernels under the SIMT interpreter as a ThreadSanitizer subject
-// (built with -fsanitize=thread -DEMU_TSAN by tests/test_kernel_emu.py; TEST INFRASTRUCTURE ONLY).
+// tsan_check.cpp -- the pipe-engine kernel under the SIMT interpreter as a ThreadSanitizer subject
+// (built with -fsanitize=thread -DEMU_TSAN by tests/test_pipe_emu.py; TEST INFRASTRUCTURE ONLY).
 // Every CUDA thread is a TSan fiber, barriers / warp collectives / mbarrier phases are release-acquire
 // edges, so any shared- or global-memory access of the kernels that is not ordered by one of them is
 // reported as a data race (exit code 66).  Results are also checked against a sequential SpMV.
-#include "tile_emu.cpp"
+#include "pipe_emu.cpp"
 
 #include <cstdio>
 #include <random>
 
-extern "C" int emu_csrmv_f64(const double*, const int*, const int*, const double*, double*, int, int, double, double, int,
-                             int, int*, int);
 extern "C" int emu_csrmv_f32(const float*, const int*, const int*, const float*, float*, int, int, float, float, int, int,
                              int*, int);
 
@@ -39,14 +37,18 @@ static int run_case(int rows, int cols, double mean_len, double empty, int long_
         for (int k = ro[r]; k < ro[r + 1]; ++k) want[r] += val[k] * x[col[k]];
     if (col.empty()) col.push_back(0);
     int bad = 0;
-    for (int mode : {0, 1, 3}) {
+    for (int mode = 0; mode < 4; ++mode) {  // grid of 1 / 3 / one block per tile, in-kernel search; 2 blocks, search kernel
+        const int blocks = mode == 0 ? 1 : mode == 1 ? 3 : mode == 2 ? (1 << 20) : 2;
+        const int search = mode != 3;
         std::vector<T> y(rows, T(-1));
         int stats[4];
         int rc;
         if constexpr (sizeof(T) == 8)
-            rc = emu_csrmv_f64(val.data(), ro.data(), col.data(), x.data(), y.data(), rows, nnz, 1.0, 0.0, 0, 0, stats, mode);
+            rc = emu_pipe_f64(val.data(), ro.data(), col.data(), x.data(), y.data(), rows, nnz, 1.0, 0.0, 0, blocks, search,
+                              nullptr, stats);
         else
-            rc = emu_csrmv_f32(val.data(), ro.data(), col.data(), x.data(), y.data(), rows, nnz, 1.f, 0.f, 0, 0, stats, mode);
+            rc = emu_pipe_f32(val.data(), ro.data(), col.data(), x.data(), y.data(), rows, nnz, 1.f, 0.f, 0, blocks, search,
+                              nullptr, stats);
         if (rc != 0 || y != want) {
             std::printf("MISMATCH rows=%d cols=%d nnz=%d mode=%d\n", rows, cols, nnz, mode);
             ++bad;

@@ -28,17 +28,24 @@ from merge_spmv_b200.csrmv import DeviceSpmv, csrmv_config
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
-ENGINES = ("stream", "tile")
+# Every kernel shape the library ships, and both launch modes: "A" / "B" = the two instantiations the
+# dispatch picks from by average row length (forced here, so each sees every structure), "A2" = A with
+# the tile coordinates from the stand-alone search kernel (two launches) instead of the producer warp.
+ENGINES = ("A", "B", "A2")
+_MODE = {"A": (1, 1), "B": (2, 1), "A2": (1, 0), "auto": (-1, -1)}
 
 
 @pytest.fixture(autouse=True)
 def _default_engine():
     yield
-    ms.lib().mspmv_set_engine(b"auto")
+    set_engine("auto")
 
 
 def set_engine(name):
-    assert ms.lib().mspmv_set_engine(name.encode()) == 0
+    cfg, search = _MODE[name]
+    L = ms.lib()
+    assert L.mspmv_set_option(b"pipe_config", cfg) == 0
+    assert L.mspmv_set_option(b"pipe_search", search) == 0
 
 
 def gpu_csrmv(ro, col, val, x, **kw):
@@ -144,26 +151,37 @@ def test_coordinates_bit_exact(orc):
         assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("engine", ("A", "B"))
 @pytest.mark.parametrize("dt,vb", [(torch.float32, 4), (torch.float64, 8)])
-def test_in_kernel_swath_coordinates_bit_exact(orc, dt, vb):
-    """The coordinates each threadblock derives in-kernel (32-ary warp search) equal thread g of
-    OmpMergeCsrmv with p = #threadblocks (cpu_spmv.cpp:311-321), and equal the debug export."""
-    set_engine("stream")
-    m = gen.make_config("powerlaw_2m", scale=1 / 16, dtype=dt).to(DEV)
-    x = torch.ones(m.cols, dtype=dt, device=DEV)
-    y = torch.empty(m.rows, dtype=dt, device=DEV)
-    err, nbytes = DeviceSpmv.CsrMV(None, 0, None, None, None, None, None, m.rows, m.cols, m.nnz, dtype=dt)
-    assert err == 0
-    temp = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
-    assert temp.data_ptr() % 256 == 0
-    err, _ = DeviceSpmv.CsrMV(temp, nbytes, m.val, m.row_offsets, m.col, x, y, m.rows, m.cols, m.nnz)
-    assert err == 0
-    torch.cuda.synchronize()
-    g = csrmv_config(vb, m.rows, m.nnz)["swaths"]
-    in_kernel = temp[: (g + 1) * 8].view(torch.int32).view(-1, 2).cpu().numpy()
-    want = orc.thread_coords(g, m.row_offsets.cpu().numpy())
-    assert np.array_equal(in_kernel, want)
-    assert np.array_equal(ms.swath_coords(m.row_offsets, vb).cpu().numpy(), want)
+def test_in_kernel_swath_coordinates_bit_exact(orc, engine, dt, vb):
+    """The tile coordinates the producer warps derive in-kernel (32-ary warp search for the first tile
+    of a block, windowed bounded search for the rest) equal the reference's MergePathSearch on the
+    tile diagonals (cpu_spmv.cpp:223-245), and equal the debug export of the stand-alone search kernel."""
+    set_engine(engine)
+    L = ms.lib()
+    for name, scale in (("powerlaw_2m", 1 / 16), ("banded_10m", 1 / 64), ("uniform_1m_64", 1 / 32)):
+        m = gen.make_config(name, scale=scale, dtype=dt).to(DEV)
+        x = torch.ones(m.cols, dtype=dt, device=DEV)
+        y = torch.empty(m.rows, dtype=dt, device=DEV)
+        err, nbytes = DeviceSpmv.CsrMV(None, 0, None, None, None, None, None, m.rows, m.cols, m.nnz, dtype=dt)
+        assert err == 0
+        temp = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+        assert temp.data_ptr() % 256 == 0
+        assert L.mspmv_set_option(b"pipe_export_coords", 1) == 0
+        try:
+            err, _ = DeviceSpmv.CsrMV(temp, nbytes, m.val, m.row_offsets, m.col, x, y, m.rows, m.cols, m.nnz)
+        finally:
+            L.mspmv_set_option(b"pipe_export_coords", 0)
+        assert err == 0
+        torch.cuda.synchronize()
+        cfg = csrmv_config(vb, m.rows, m.nnz)
+        t, tile = cfg["tiles"], cfg["tile_items"]
+        in_kernel = temp[: (t + 1) * 8].view(torch.int32).view(-1, 2).cpu().numpy()
+        ro = m.row_offsets.cpu().numpy()
+        diags = np.minimum(np.arange(t + 1, dtype=np.int64) * tile, m.rows + m.nnz)
+        want = np.array([orc.merge_path_search(int(d), ro) for d in diags], np.int32)
+        assert np.array_equal(in_kernel, want), name
+        assert np.array_equal(ms.swath_coords(m.row_offsets, vb).cpu().numpy(), want), name
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -365,9 +383,13 @@ def test_launch_counter_and_config():
     L = ms.lib()
     m = gen.make_config("uniform_1m_64", scale=1 / 64).to(DEV)
     x = torch.ones(m.cols, dtype=torch.float64, device=DEV)
-    set_engine("stream")
     before = L.mspmv_launch_count()
     ms.csrmv(m.row_offsets, m.col, m.val, x)
     cfg = csrmv_config(8, m.rows, m.nnz)
-    assert L.mspmv_launch_count() - before == cfg["kernels_per_call"] == 2
-    assert cfg["threads"] % 32 == 0 and cfg["swaths"] <= 4 * torch.cuda.get_device_properties(0).multi_processor_count
+    assert L.mspmv_launch_count() - before == cfg["kernels_per_call"] == 1  # one launch per CsrMV
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert cfg["threads"] % 32 == 0 and cfg["blocks"] <= min(cfg["tiles"], 32 * sms)
+    set_engine("A2")
+    before = L.mspmv_launch_count()
+    ms.csrmv(m.row_offsets, m.col, m.val, x)
+    assert L.mspmv_launch_count() - before == csrmv_config(8, m.rows, m.nnz)["kernels_per_call"] == 2

@@ -49,21 +49,3 @@ def test_shard_partition_invariants(lengths, p):
         # complete rows of the shard keep their ends; the first local row may be a row's tail
         for i in range(x1 - x0):
             assert lro[i + 1] == ro[x0 + i + 1] - y0
-
-
-def test_lsu_model_smoke():
-    """tools/lsu_model.py (static count of LSU wavefronts per tile for both tile-kernel variants) runs
-    from the generators alone and reproduces the committed banded numbers (profiles/lsu_model_r01.txt):
-    variant 3 trades shared-memory wavefronts for gather lines on short rows."""
-    import os
-    import subprocess
-    import sys
-
-    from conftest import ROOT
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "lsu_model.py"), "--tiles", "2", "--workloads",
-                          "banded_10m"], capture_output=True, text=True, check=True, timeout=300).stdout
-    rows = [l.split() for l in out.splitlines() if l.startswith("banded_10m")]
-    assert len(rows) == 2
-    v2, v3 = ({"smem": float(r[2]), "lines": float(r[3])} for r in rows)
-    assert v3["smem"] < v2["smem"] and v3["lines"] > v2["lines"]
-    assert abs(v2["smem"] - 519) <= 5 and abs(v3["smem"] - 407) <= 5

@@ -36,7 +36,7 @@ def build(name, extra=()):
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, f"libpipe_emu_{name}.so")
     srcs = [os.path.join(EMU, f) for f in ("pipe_emu.cpp", "simt_emu.hpp", "ptx_emu.cuh")]
-    srcs += [os.path.join(CSRC, f) for f in ("spmv_pipe.cuh", "spmv_tile.cuh", "merge_common.cuh", "tma_stage.cuh",
+    srcs += [os.path.join(CSRC, f) for f in ("spmv_pipe.cuh", "merge_search.cuh", "carry_exchange.cuh", "merge_common.cuh", "tma_stage.cuh",
                                              "ptx_sm100.cuh")]
     if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(s) for s in srcs + [__file__]):
         return out
@@ -364,3 +364,63 @@ def test_pipe_address_sanitizer():
     r = subprocess.run([sys.executable, os.path.join(EMU, "pipe_asan_check.py"), lib], capture_output=True, text=True,
                        env=env, timeout=900)
     assert r.returncode == 0 and "asan check complete" in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+
+
+def test_pipe_thread_sanitizer():
+    """Data-race check of the kernels' shared-memory protocol.  tests/emu/tsan_check.cpp builds the
+    interpreter with -fsanitize=thread -DEMU_TSAN: every CUDA thread is a TSan fiber, __syncthreads /
+    named barriers / warp collectives / mbarrier phases are the only release-acquire edges, atomics are
+    atomics, the bytes a bulk copy lands are ordinary writes.  Any access of the pipe kernel (every
+    thread role: producer, consumers, the last block's fold) or the carry exchange that is not ordered by those edges is reported
+    (removing the barrier after the row-end scatter, or the mbarrier wait, gives dozens of reports)."""
+    import shutil
+
+    gxx = shutil.which("g++")
+    libtsan = subprocess.run([gxx, "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(libtsan):
+        pytest.skip("libtsan not available")
+    out_dir = os.path.join(EMU, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "tsan_check")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fno-strict-aliasing", "-ffp-contract=off", "-w",
+                    "-fsanitize=thread", "-DEMU_TSAN", "-I", EMU, "-I", CSRC, "-I", "/usr/local/cuda/include",
+                    os.path.join(EMU, "tsan_check.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
+    if "unexpected memory mapping" in r.stderr or "FATAL: ThreadSanitizer" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot start in this environment: " + r.stderr[-200:])
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+    assert r.returncode == 0 and "tsan check complete" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
+@pytest.mark.parametrize("use_f32", [0, 1])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_pipe_nvlink_carry_exchange(emu0, world, use_f32):
+    """carry_exchange_kernel (peer-memory push + flag, then wait + fold) with `world` simulated
+    ranks over several steps: slot indexing, the epoch-parity double buffer, the fold order of
+    cpu_spmv.cpp:348-352 (a row spanning several ranks takes every carry; carries of rows >= rows
+    are dropped; the last rank's carry is never applied)."""
+    rng = np.random.default_rng(world)
+    steps = 5
+    rows = 40
+    cuts = np.zeros(world + 1, np.int32)
+    cuts[1:-1] = np.sort(rng.integers(0, rows + 1, world - 1))
+    cuts[-1] = rows
+    if world == 8:
+        cuts[3] = cuts[4] = cuts[5]  # ranks 3 and 4 own no row: one long row spans them
+    carry_rows = np.ascontiguousarray(cuts[1:]).astype(np.int32)  # rank g's carry belongs to global row cuts[g+1]
+    carries = rng.integers(1, 50, (steps, world)).astype(np.float64)
+    y = np.zeros((steps, rows), np.float64)
+    lib = emu0.lib
+    lib.emu_exchange_f64.restype = C.c_int
+    lib.emu_exchange_f64.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = lib.emu_exchange_f64(world, steps, cuts.ctypes.data, carry_rows.ctypes.data, carries.ctypes.data,
+                              y.ctypes.data, use_f32)
+    assert rc == 0, "every rank must have advanced its epoch counter once per step"
+    for st in range(steps):
+        want = 100.0 * st + np.arange(rows, dtype=np.float64)
+        for g in range(world - 1):
+            r = int(carry_rows[g])
+            if r < rows:
+                want[r] += carries[st, g]
+        assert np.array_equal(y[st], want), (st, cuts.tolist())
