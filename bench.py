@@ -28,6 +28,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# Thread placement of the CPU legs (cpu_baseline, --impl reference): BASELINE.md section 4 prescribes
+# OMP_PROC_BIND=spread OMP_PLACES=cores for the reference's OpenMP loop (its own KMP_AFFINITY is
+# Intel-runtime-only).  libgomp reads these once, when it is first loaded -- i.e. before torch is imported.
+os.environ.setdefault("OMP_PROC_BIND", "spread")
+os.environ.setdefault("OMP_PLACES", "cores")
+OMP_BINDING = f"OMP_PROC_BIND={os.environ['OMP_PROC_BIND']} OMP_PLACES={os.environ['OMP_PLACES']}"
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -184,9 +191,11 @@ def run_reference(args):
         return 0
     from merge_spmv_b200 import generators as gen
 
-    name, kind, dt, p, scaling = workload_spec(args.workload, 1)
+    # the same N-scaled shape as the GPU arm; the CPU then times a bounded sample of it (leading rows)
+    name, kind, dt, p, scaling = workload_spec(args.workload, max(args.gpus, 1))
     ro, cols, _ = build_row_offsets(kind, p)
     vb = 8 if dt == torch.float64 else 4
+    full_rows, full_nnz = ro.numel() - 1, int(ro[-1])
     # bounded sample: cap the matrix so K+W steps finish within a few minutes on slow hosts
     budget_nnz = int(os.environ.get("MSPMV_REF_MAX_NNZ", 1 << 26))
     ro_s, col, val, rows, nnz = host_sample(kind, dt, p, ro, cols, args.values, budget_nnz)
@@ -216,14 +225,63 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f64" if vb == 8 else "f32", "data": "synthetic",
-        "config": {"workload": name, "rows": rows, "cols": cols, "nnz": nnz, "values": args.values,
-                   "l2": "inputs larger than L2"},
-        "cpu_baseline": {"value": gflops, "unit": UNIT, "cores": threads, "kind": kindname, "sample": sample},
+        "config": {"workload": name, "rows": full_rows, "cols": cols, "nnz": full_nnz, "values": args.values,
+                   "sample_rows": rows, "sample_nnz": nnz, "l2": "inputs larger than L2"},
+        "cpu_baseline": {"value": gflops, "unit": UNIT, "cores": threads, "kind": kindname, "sample": sample,
+                         "binding": OMP_BINDING},
         "e2e": {"value": gflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# parity inside the bench (outside the timed region): this rank's rows against an fp64 reference
+# --------------------------------------------------------------------------------------------------
+def check_parity(kind, ro, cols, dt, p, shard, x, y_owned, values, dev, chunk_nnz=1 << 25):
+    """y_owned = global rows [shard.x0, shard.x1) as computed by the (sharded) CsrMV.  The reference
+    regenerates those rows' nonzeros (the generators are counter-based, so any range can be rebuilt),
+    accumulates val*x[col] per row in fp64 on the device (index_add), and is compared with the tolerances of
+    tests/test_gpu_parity.py: exact for all-ones inputs, fp64 1e-10 relative, fp32
+    max(1e-6, 4*sqrt(row length)*2^-24) relative."""
+    x0, x1 = shard.x0, shard.x1
+    n = x1 - x0
+    if n == 0:
+        return {"ok": True, "max_rel": 0.0, "rows_checked": 0, "tol": "n/a (rank owns no row)"}
+    ro64 = ro.to(torch.int64)
+    lens = (ro64[x0 + 1: x1 + 1] - ro64[x0: x1]).to(dev)
+    if values == "ones":
+        ok = bool(torch.equal(y_owned, lens.to(dt)))
+        return {"ok": ok, "max_rel": 0.0 if ok else float("inf"), "rows_checked": n,
+                "tol": "bit-exact: y == row lengths (values = x = 1, gpu_spmv.cu:521-525)"}
+    ref = torch.zeros(n, dtype=torch.float64, device=dev)
+    xd = x.double()
+    r = x0
+    while r < x1:  # whole rows per chunk, about chunk_nnz nonzeros each
+        k0 = int(ro64[r])
+        r_hi = int(torch.searchsorted(ro64, torch.tensor(k0 + chunk_nnz), right=True)) - 1
+        r_hi = min(max(r_hi, r + 1), x1)
+        k1 = int(ro64[r_hi])
+        if k1 > k0:
+            col, val = fill(kind, ro, cols, k0, k1, dt, values, dev, p)
+            rl = (ro64[r + 1: r_hi + 1] - ro64[r: r_hi]).to(dev)
+            rid = torch.repeat_interleave(torch.arange(r - x0, r_hi - x0, device=dev), rl)
+            ref.index_add_(0, rid, val.double() * xd[col.long()])
+            del col, val, rid
+        r = r_hi
+    err = (y_owned.double() - ref).abs()
+    scale = ref.abs().clamp_min(1e-300)
+    if dt == torch.float64:
+        tol = torch.full_like(ref, 1e-10)
+        tol_s = "fp64: |y - ref| <= 1e-10 |ref|"
+    else:
+        tol = torch.clamp(4 * torch.sqrt(lens.double()) * 2.0 ** -24, min=1e-6)
+        tol_s = "fp32: |y - ref| <= max(1e-6, 4 sqrt(row length) 2^-24) |ref|"
+    rel = err / scale
+    ok = bool((rel <= tol).all()) and bool(torch.isfinite(y_owned).all())
+    return {"ok": ok, "max_rel": float(rel.max()), "rows_checked": n, "tol": tol_s,
+            "reference": "fp64 index_add of val*x[col] over the rank's rows, on the device"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -246,10 +304,11 @@ def main():
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
                     help="N>1: how the carries travel -- nccl: one all_gather + fold kernel (default); p2p: one kernel "
                          "per rank storing into the peers' symmetric memory over NVLink (csrc/carry_exchange.cuh)")
-    ap.add_argument("--e2e-pipeline", action="store_true",
-                    help="N>1: overlap the host->device copy of x, the sharded product and the device->host copy of the "
-                         "y slice over three streams and three buffer slots (what mspmv_session_apply_many does at N=1); "
-                         "default: one step after the other")
+    ap.add_argument("--e2e-sequential", action="store_true",
+                    help="N>1: run the end-to-end steps one after the other instead of the default three-stream "
+                         "pipeline (H2D of x | broadcast + product | D2H of the y slice over three buffer slots)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra_workloads (BASELINE configs 3, 4 at N=1; config 5 at every N)")
     ap.add_argument("--gather-y", action="store_true",
                     help="N>1: include the all_gather of the y slices in every step (solver-style: the whole y "
                          "on every rank, ready to be the next x)")
@@ -289,19 +348,11 @@ def main():
             raise SystemExit(f"unknown option {kv!r}")
         options[k] = int(v)
 
-    name, kind, dt, p, scaling = workload_spec(args.workload, world)
-    if args.cols:
-        p["cols"] = args.cols
-    vb = 8 if dt == torch.float64 else 4
-    ro, cols, alpha = build_row_offsets(kind, p)
-    rows, nnz = ro.numel() - 1, int(ro[-1])
-    ro_np = ro.numpy()
-    xmode = "ones" if args.values == "ones" else "random"
-    x = gen.vector(cols, dt, xmode, device=dev)
-
-    shard = sharded.make_shard(ro_np, cols, rank, world,
-                               lambda k0, k1: fill(kind, ro, cols, k0, k1, dt, args.values, dev, p), dev)
-    op = sharded.ShardedSpmv(shard, exchange=args.exchange if world > 1 else "nccl")
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     L = ms.lib()
 
     def barrier():
@@ -309,80 +360,115 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = args.graph in ("on", "auto")
-    c0 = L.mspmv_launch_count()
-    op(x)  # one eager step: also counts this library's kernels per step (graph replays bypass the counter)
-    launches_per_step = L.mspmv_launch_count() - c0
-    gather_y = bool(args.gather_y and world > 1)
-    if use_graph:
-        step = op.capture(x, gather_y=gather_y)
-    else:
-        step = (lambda: op.matvec_full(x)) if gather_y else (lambda: op(x))
+    def measure(wname, steps, warmup, gather_y=False):
+        """Build the workload, run warm-up + parity check + the timed region.  Returns a dict with the
+        device-timed numbers plus the live objects (op, x, y, shard ...) the e2e / CPU legs re-use."""
+        name, kind, dt, p, scaling = workload_spec(wname, world)
+        if args.cols and wname == args.workload:
+            p["cols"] = args.cols
+        vb = 8 if dt == torch.float64 else 4
+        ro, cols, alpha = build_row_offsets(kind, p)
+        rows, nnz = ro.numel() - 1, int(ro[-1])
+        ro_np = ro.numpy()
+        x = gen.vector(cols, dt, "ones" if args.values == "ones" else "random", device=dev)
+        shard = sharded.make_shard(ro_np, cols, rank, world,
+                                   lambda k0, k1: fill(kind, ro, cols, k0, k1, dt, args.values, dev, p), dev)
+        op = sharded.ShardedSpmv(shard, exchange=args.exchange if world > 1 else "nccl")
+        use_graph = args.graph in ("on", "auto")
+        c0 = L.mspmv_launch_count()
+        op(x)  # one eager step: also counts this library's kernels per step (graph replays bypass the counter)
+        launches_per_step = L.mspmv_launch_count() - c0
+        gy = bool(gather_y and world > 1)
+        if use_graph:
+            step = op.capture(x, gather_y=gy)
+        else:
+            step = (lambda: op.matvec_full(x)) if gy else (lambda: op(x))
 
-    # ---- warm-up + correctness guard (exact identity on ones; finite on random) ----------------
-    for _ in range(args.warmup):
-        y = step()
-    torch.cuda.synchronize()
-    if args.values == "ones":
-        lo, hi = (0, rows) if gather_y else (shard.x0, shard.x1)
-        lens = torch.diff(torch.from_numpy(ro_np[lo: hi + 1])).to(dt).to(dev)
-        assert torch.equal(y, lens), "warm-up result is not the row-length vector"
-    else:
-        assert bool(torch.isfinite(y).all())
+        # ---- warm-up, then parity OUTSIDE the timed region: this rank's rows against an fp64 reference
+        for _ in range(warmup):
+            y = step()
+        torch.cuda.synchronize()
+        y_owned = y[shard.x0:shard.x1] if gy else y
+        parity = check_parity(kind, ro, cols, dt, p, shard, x, y_owned, args.values, dev)
+        if world > 1:
+            flag = torch.tensor([0 if parity["ok"] else 1], dtype=torch.int32, device=dev)
+            worst = torch.tensor([parity["max_rel"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(flag)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            parity["ok"] = bool(flag.item() == 0)
+            parity["max_rel"] = float(worst.item())
+            parity["ranks"] = world
+        if not parity["ok"]:
+            raise SystemExit(f"parity check failed on {name}: {parity}")
 
-    # ---- timed region: exactly K steps, events on the launching stream, max over ranks ---------
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    launches0 = L.mspmv_launch_count()
-    with sampler:
-        start.record()
-        for _ in range(args.steps):
-            step()
-        stop.record()
-        stop.synchronize()
-    launches = L.mspmv_launch_count() - launches0
-    if use_graph:
-        launches = launches_per_step * args.steps  # replayed from the captured graph
-    barrier()
-    elapsed_ms = start.elapsed_time(stop)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
-    ms_per_step = elapsed_ms / args.steps
-    gflops = 2.0 * nnz / ms_per_step / 1e6
+        # ---- timed region: exactly K steps, events on the launching stream, max over ranks ---------
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        launches0 = L.mspmv_launch_count()
+        with sampler:
+            start.record()
+            for _ in range(steps):
+                step()
+            stop.record()
+            stop.synchronize()
+        launches = L.mspmv_launch_count() - launches0
+        if use_graph:
+            launches = launches_per_step * steps  # replayed from the captured graph
+        barrier()
+        elapsed_ms = start.elapsed_time(stop)
+        if world > 1:
+            t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t.item())
+            lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+            dist.all_reduce(lt)
+            launches = int(lt.item())
+        ms_per_step = elapsed_ms / steps
+        gflops = 2.0 * nnz / ms_per_step / 1e6
 
-    # ---- roofline of the dominant kernel (per rank: its shard's compulsory bytes / step time) --
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    shard_bytes = algorithmic_bytes(shard.local_rows, cols, shard.nnz, vb)
-    achieved = shard_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{name}@{world}")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "spmv_pipe_kernel",
-                "algorithmic_bytes_per_launch": shard_bytes,
-                "frac_of_nominal_8000_gbs": achieved / 8000.0,  # BASELINE.md section 2 also asks for the nominal figure
-                "note": "duration = whole step (search + tile + carry fix-up kernels; the tile kernel is 94.7% of it, profiles/launches_r01.csv), CUDA events"}
+        # ---- roofline of the dominant kernel (per rank: its shard's compulsory bytes / step time) --
+        shard_bytes = algorithmic_bytes(shard.local_rows, cols, shard.nnz, vb)
+        achieved = shard_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"{name}@{world}")
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": "profiles/traffic.json: ncu dram__bytes_read+write of this kernel "
+                                                          "build (static; tests/test_abi.py pins the SASS it was taken with)",
+                    "peak_source": peak_src, "kernel": "spmv_pipe_kernel",
+                    "algorithmic_bytes_per_launch": shard_bytes,
+                    "frac_of_nominal_8000_gbs": achieved / 8000.0,  # BASELINE.md section 2 also asks for the nominal figure
+                    "note": "one kernel per CsrMV (search, tiles and carry fold inside it); duration = whole step, CUDA events"}
+        if kind in ("uniform", "powerlaw"):
+            # Random columns: every nonzero costs one 32-byte sector request of x, and one SM sends ONE
+            # request per clock to the L2 crossbar (ncu l1tex__m_l1tex2xbar_req_cycles_active; TMA bulk
+            # loads share that port at one 128-byte request each).  That, not HBM, is the binding limit of
+            # these workloads (profiles/gather_ceiling_r02.txt); reported beside the HBM roofline so frac
+            # can be read against the right ceiling.
+            sm_clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            requests = shard.nnz + (shard.nnz * (vb + 4) + shard.local_rows * 4) / 128.0
+            r_rate = requests / (ms_per_step * 1e-3) / 1e9
+            roofline["secondary"] = {"bound": "SM->L2 request port (1 request/clk/SM): one 32 B sector per x[col] gather "
+                                              "+ one per 128 B of TMA tile data",
+                                     "achieved": r_rate, "peak": sms * sm_clk / 1e9, "unit": "G requests/s",
+                                     "frac": r_rate / (sms * sm_clk / 1e9),
+                                     "peak_source": "148 SMs x SM clock during the run; counter evidence in "
+                                                    "profiles/gather_ceiling_r02.txt"}
+        return dict(name=name, kind=kind, dt=dt, p=p, scaling=scaling, vb=vb, ro=ro, ro_np=ro_np, cols=cols, rows=rows,
+                    nnz=nnz, alpha=alpha, x=x, y=y, shard=shard, op=op, step=step, use_graph=use_graph, gather_y=gy,
+                    ms_per_step=ms_per_step, gflops=gflops, launches=int(launches), roofline=roofline,
+                    achieved=achieved, shard_bytes=shard_bytes, parity=parity, clocks=sampler.summary())
 
-    if kind in ("uniform", "powerlaw"):
-        # Random columns: every nonzero costs one 32-byte L2->L1 sector of x, and one SM retires
-        # ~0.93 such L1-miss sectors per clock (profiles/microbench_r01.txt: 270 G gathers/s chip-wide
-        # for any L2-resident table, fp32 == fp64).  That, not HBM, is the binding limit of these
-        # workloads; reported beside the HBM roofline so frac can be read against the right ceiling.
-        g_rate = shard.nnz / (ms_per_step * 1e-3) / 1e9
-        roofline["secondary"] = {"bound": "l1tex gather sectors (random x[col])", "achieved": g_rate,
-                                 "peak": 270.0, "unit": "G gathers/s", "frac": g_rate / 270.0,
-                                 "peak_source": "profiles/microbench_r01.txt (measured on this pool's B200)"}
+    m = measure(args.workload, args.steps, args.warmup, gather_y=args.gather_y)
+    name, kind, dt, p, scaling, vb = m["name"], m["kind"], m["dt"], m["p"], m["scaling"], m["vb"]
+    ro, ro_np, cols, rows, nnz, alpha = m["ro"], m["ro_np"], m["cols"], m["rows"], m["nnz"], m["alpha"]
+    x, y, shard, op = m["x"], m["y"], m["shard"], m["op"]
+    use_graph, gather_y = m["use_graph"], m["gather_y"]
+    ms_per_step, gflops, launches, roofline = m["ms_per_step"], m["gflops"], m["launches"], m["roofline"]
+    achieved, shard_bytes, parity_main = m["achieved"], m["shard_bytes"], m["parity"]
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------
     e2e = None
@@ -413,11 +499,13 @@ def main():
                    "api": "mspmv_session_apply_many (pinned host x in, host y out, 3-stage pipeline)",
                    "unpipelined_ms_per_step": single_ms, "matrix_upload_ms": setup_ms,
                    "matrix_upload_bytes": int(nnz * (vb + 4) + (rows + 1) * 4)}
-        elif args.e2e_pipeline:
-            # H2D(i+1) | product(i) | D2H(i-1) on three streams over K slots; the collective runs on the
-            # compute stream like the kernels.  Same bytes per step as the sequential form below.
+        else:
+            # N > 1.  x arrives in ONE host buffer (rank 0, pinned): it crosses PCIe once and is then
+            # broadcast over NVLink (NCCL) -- not uploaded N times -- and every rank returns its slice of y
+            # to its own pinned host buffer.  Three streams over K slots:  H2D(i+1) | bcast + product(i) | D2H(i-1)
+            # (what mspmv_session_apply_many does at N=1).  --e2e-sequential: one step after the other.
             K = 3
-            xh = x.cpu().pin_memory()
+            xh = x.cpu().pin_memory() if rank == 0 else None
             s_h2d, s_comp, s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
             xds = [torch.empty_like(x) for _ in range(K)]
             yds = [torch.empty(shard.owned_rows, dtype=dt, device=dev) for _ in range(K)]
@@ -432,12 +520,14 @@ def main():
                     with torch.cuda.stream(s_h2d):
                         if i >= K:
                             s_h2d.wait_event(ev_k[sl])   # the product that read this x slot is done
-                        xds[sl].copy_(xh, non_blocking=True)
+                        if rank == 0:
+                            xds[sl].copy_(xh, non_blocking=True)
                         ev_x[sl].record(s_h2d)
                     with torch.cuda.stream(s_comp):
                         s_comp.wait_event(ev_x[sl])
                         if i >= K:
                             s_comp.wait_event(ev_y[sl])  # the copy that drained this y slot is done
+                        dist.broadcast(xds[sl], src=0)   # NVLink, ordered on the compute stream
                         yds[sl].copy_(op(xds[sl]))
                         ev_k[sl].record(s_comp)
                     with torch.cuda.stream(s_d2h):
@@ -447,31 +537,32 @@ def main():
                 for st in (s_h2d, s_comp, s_d2h):
                     st.synchronize()
 
+            def run_sequential(n):
+                for i in range(n):
+                    if rank == 0:
+                        xds[0].copy_(xh, non_blocking=True)
+                    dist.broadcast(xds[0], src=0)
+                    yhs[0].copy_(op(xds[0]), non_blocking=True)
+                torch.cuda.synchronize()
+
+            run = run_sequential if args.e2e_sequential else run_pipelined
             torch.cuda.synchronize()
-            run_pipelined(K)  # warm
+            run(K)  # warm
             barrier()
             t0 = time.perf_counter()
-            run_pipelined(n_e2e)
+            run(n_e2e)
             barrier()
             dt_s = time.perf_counter() - t0
-            assert torch.equal(yhs[(n_e2e - 1) % K].to(dev), y if not gather_y else y[shard.x0:shard.x1])
-        else:
-            xh = x.cpu().pin_memory()
-            yh = torch.empty(shard.owned_rows, dtype=dt).pin_memory()
-            xd = torch.empty_like(x)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(n_e2e):
-                xd.copy_(xh, non_blocking=True)
-                yh.copy_(op(xd), non_blocking=True)
-            barrier()
-            dt_s = time.perf_counter() - t0
+            last = yhs[0] if args.e2e_sequential else yhs[(n_e2e - 1) % K]
+            assert torch.equal(last.to(dev), y if not gather_y else y[shard.x0:shard.x1])
             tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e = {"value": 2.0 * nnz * n_e2e / float(tt.item()) / 1e9, "unit": UNIT,
-                   "h2d_bytes_per_step": cols * vb, "d2h_bytes_per_step": shard.owned_rows * vb,
-                   "steps": n_e2e, "api": "ShardedSpmv with pinned host x / y per rank"
-                                          + (", three-stream pipeline" if args.e2e_pipeline else ", sequential")}
+                   "h2d_bytes_per_step": cols * vb, "d2h_bytes_per_step": rows * vb, "steps": n_e2e,
+                   "api": "ShardedSpmv: pinned host x on rank 0 -> one H2D -> NCCL broadcast over NVLink -> sharded CsrMV "
+                          "-> every rank's y slice D2H to pinned host memory"
+                          + (", sequential" if args.e2e_sequential else ", three-stream pipeline over 3 slots"),
+                   "bytes_note": "h2d = x once (rank 0); d2h = all ranks' slices together"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------
     cpu = None
@@ -480,9 +571,34 @@ def main():
         ro_s, col_s, val_s, rows_s, nnz_s = host_sample(kind, dt, p, ro, cols, args.values, budget_nnz)
         c = cpu_time(ro_s, col_s, val_s, x.cpu().numpy(), budget_s=15.0)
         cpu = {"value": c["gflops"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
-               "ms_per_step": c["ms"],
+               "ms_per_step": c["ms"], "binding": OMP_BINDING,
                "sample": f"first {rows_s} rows / {nnz_s} nnz of {name} "
                          f"({'full workload' if nnz_s == nnz else 'bounded sample'}), {c['iters']} timed calls"}
+
+    # ---- extra workloads: the other BASELINE.json configs, device-timed with parity, in the same line ----
+    # N=1: config 3 (power-law fp32) and config 4 (banded fp64); every N: config 5 (20M x 20M power-law,
+    # 1B nnz) sharded over the N GPUs -- "strong": the 8-GPU / 1-GPU ratio of its value is the north-star's >= 6x.
+    extras = []
+    if not args.no_extras and args.workload in ("default", "uniform_1m_64"):
+        main_clocks = m["clocks"]
+        step = None
+        del m, op, shard, x, y
+        torch.cuda.empty_cache()
+        names = (["powerlaw_2m", "banded_10m"] if world == 1 else []) + ["powerlaw_20m"]
+        for wn in names:
+            k = 30 if wn == "powerlaw_20m" else 100
+            e = measure(wn, k, 5)
+            extras.append({"workload": e["name"], "dtype": "f64" if e["vb"] == 8 else "f32", "rows": e["rows"],
+                           "cols": e["cols"], "nnz": e["nnz"], "scaling": "strong" if world > 1 else e["scaling"],
+                           "steps": k, "ms_per_step": e["ms_per_step"], "value": e["gflops"], "unit": UNIT,
+                           "roofline_frac": e["roofline"]["frac"], "hbm_gbs_algorithmic": e["achieved"] * world,
+                           "request_port_frac": (e["roofline"].get("secondary") or {}).get("frac"),
+                           "parity": e["parity"], "clocks": e["clocks"], "gpu_launches": e["launches"]})
+            e["step"] = None
+            del e
+            torch.cuda.empty_cache()
+    else:
+        main_clocks = m["clocks"]
 
     if rank == 0:
         line = {
@@ -496,8 +612,8 @@ def main():
                        "l2": "inputs larger than L2 (no flush)" if shard_bytes > 200e6 else "inputs fit L2",
                        "engine": "pipe", "cuda_graph": use_graph, "gather_y": gather_y, "options": options,
                        "carry_exchange": (args.exchange if world > 1 else None)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
+            "roofline": roofline, "parity": parity_main, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": main_clocks, "extra_workloads": extras,
             "hbm_gbs_algorithmic": achieved * (1 if world == 1 else world),
         }
         if alpha is not None:
@@ -509,7 +625,6 @@ def main():
         sys.stdout.flush()
         torch.cuda.synchronize()
         dist.barrier()
-        step = None
         if use_graph:
             os._exit(0)
         dist.destroy_process_group()

@@ -98,24 +98,40 @@ class DeviceSpmv:
 
 
 _temp_cache = {}
+_temp_retired = []  # superseded blobs stay alive: a captured CUDA graph or an in-flight call may still use them
 
 
 def _temp_for(device, nbytes):
     key = (device.index if device.index is not None else torch.cuda.current_device())
     t = _temp_cache.get(key)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            _temp_retired.append(t)
         t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
         _temp_cache[key] = t
     return t
 
 
-def csrmv(row_offsets, column_indices, values, x, y=None, *, alpha=None, beta=None, num_cols=None,
-          stream=None, debug_synchronous=False):
-    """Convenience wrapper: size query + temp blob (cached per device) + run.  Returns ``y``.
+def temp_storage(values_dtype, num_rows, num_cols, num_nonzeros, device, axpby=False):
+    """A temp blob of the size ``mspmv_csrmv_*`` asks for this shape (the caller owns it)."""
+    if axpby:
+        err, nbytes = DeviceSpmv.CsrMVAxpby(None, 0, None, None, None, None, None, num_rows, num_cols, num_nonzeros,
+                                            1.0, 0.0, dtype=values_dtype)
+    else:
+        err, nbytes = DeviceSpmv.CsrMV(None, 0, None, None, None, None, None, num_rows, num_cols, num_nonzeros,
+                                       dtype=values_dtype)
+    _lib.check(err, "CsrMV size query")
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
 
-    The cached blob is shared by every call on that device, so calls must be stream-ordered with
-    respect to each other (like any CUB temp storage); use ``DeviceSpmv.CsrMV`` with your own blobs
-    to run several CsrMVs concurrently."""
+
+def csrmv(row_offsets, column_indices, values, x, y=None, *, alpha=None, beta=None, num_cols=None,
+          stream=None, debug_synchronous=False, temp=None):
+    """Convenience wrapper: size query + temp blob + run.  Returns ``y``.
+
+    ``temp``: the caller's own blob (``temp_storage()``); anything that outlives the call -- a captured
+    CUDA graph, work on several streams -- must pass one.  Without it a blob cached per device is used:
+    it is shared by every such call on that device, so those calls must be stream-ordered with respect
+    to each other (like any CUB temp storage)."""
     rows = row_offsets.numel() - 1
     nnz = values.numel()
     cols = int(num_cols) if num_cols is not None else x.numel()
@@ -128,14 +144,16 @@ def csrmv(row_offsets, column_indices, values, x, y=None, *, alpha=None, beta=No
         err, nbytes = DeviceSpmv.CsrMVAxpby(None, 0, None, None, None, None, None, rows, cols, nnz, a, b,
                                             dtype=values.dtype)
         _lib.check(err, "CsrMV size query")
-        temp = _temp_for(values.device, nbytes)
+        if temp is None:
+            temp = _temp_for(values.device, nbytes)
         err, _ = DeviceSpmv.CsrMVAxpby(temp, temp.numel(), values, row_offsets, column_indices, x, y,
                                        rows, cols, nnz, a, b, stream, debug_synchronous)
     else:
         err, nbytes = DeviceSpmv.CsrMV(None, 0, None, None, None, None, None, rows, cols, nnz,
                                        dtype=values.dtype)
         _lib.check(err, "CsrMV size query")
-        temp = _temp_for(values.device, nbytes)
+        if temp is None:
+            temp = _temp_for(values.device, nbytes)
         err, _ = DeviceSpmv.CsrMV(temp, temp.numel(), values, row_offsets, column_indices, x, y, rows,
                                   cols, nnz, stream, debug_synchronous)
     _lib.check(err, "CsrMV")

@@ -26,7 +26,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .csrmv import _ptr, _stream, csrmv
+from .csrmv import _ptr, _stream, csrmv, temp_storage
 
 
 def partition(row_offsets_host: np.ndarray, world: int) -> np.ndarray:
@@ -142,8 +142,12 @@ class ShardedSpmv:
         self.carries = torch.zeros(shard.world, dtype=shard.val.dtype, device=dev)
         self._gathered = None  # (world, pad) receive buffer of gather_y, allocated on first use
         # injectable for the CPU (gloo) tests of the exchange logic; the defaults are the CUDA path
+        # own temp blob: a captured graph bakes its address in, so it must not be a shared, replaceable one
+        self._temp = None
+        if local_spmv is None:
+            self._temp = temp_storage(shard.val.dtype, shard.local_rows, shard.cols, shard.nnz, dev)
         self._local_spmv = local_spmv or (lambda s, x, y: csrmv(s.row_offsets, s.col, s.val, x, y,
-                                                               num_cols=s.cols))
+                                                               num_cols=s.cols, temp=self._temp))
         self._fold = fold or apply_carries
         if exchange == "p2p" and shard.world > 1:
             self._setup_p2p()
@@ -192,7 +196,7 @@ class ShardedSpmv:
                           _ptr(self._epoch), _stream(None)), "exchange_carries")
 
     def capture(self, x, gather_y=False):
-        """Record one whole step (search + tile + fix-up kernels, the all_gather, the carry fold --
+        """Record one whole step (the CsrMV kernel, the all_gather, the carry fold --
         and, with ``gather_y``, the exchange of the y slices) into a CUDA graph over the fixed
         input buffer ``x``; returns a callable that replays it with a single launch.  Removes
         per-kernel launch gaps and the host cost of the collectives."""
