@@ -389,7 +389,10 @@ def main():
             y = step()
         torch.cuda.synchronize()
         y_owned = y[shard.x0:shard.x1] if gy else y
-        parity = check_parity(kind, ro, cols, dt, p, shard, x, y_owned, args.values, dev)
+        if os.environ.get("MSPMV_BENCH_SKIP_PARITY") == "1":  # debugging aid only: the line then says so
+            parity = {"ok": True, "max_rel": float("nan"), "rows_checked": 0, "tol": "SKIPPED (MSPMV_BENCH_SKIP_PARITY)"}
+        else:
+            parity = check_parity(kind, ro, cols, dt, p, shard, x, y_owned, args.values, dev)
         if world > 1:
             flag = torch.tensor([0 if parity["ok"] else 1], dtype=torch.int32, device=dev)
             worst = torch.tensor([parity["max_rel"]], dtype=torch.float64, device=dev)
@@ -406,12 +409,27 @@ def main():
         sampler = ClockSampler(local_rank)
         barrier()
         launches0 = L.mspmv_launch_count()
+        trace = os.environ.get("MSPMV_BENCH_TRACE") == "1"  # debugging aid: one event per step, printed to stderr
+        marks = []
+        sync_token = torch.zeros(1, device=dev)
         with sampler:
+            if world > 1:
+                # device-side rendezvous right in front of the start event: the ranks leave the host barrier a
+                # few ms apart, and without this the early rank's first step would time the late rank's arrival
+                dist.all_reduce(sync_token)
             start.record()
             for _ in range(steps):
                 step()
+                if trace:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    marks.append(e)
             stop.record()
             stop.synchronize()
+        if trace:
+            ts = [start.elapsed_time(e) for e in marks]
+            print(f"[trace rank {rank}] {name}: per-step ms " +
+                  " ".join(f"{b - a:.3f}" for a, b in zip([0.0] + ts[:-1], ts)), file=sys.stderr, flush=True)
         launches = L.mspmv_launch_count() - launches0
         if use_graph:
             launches = launches_per_step * steps  # replayed from the captured graph
