@@ -532,6 +532,24 @@ def main():
             ev_k = [torch.cuda.Event() for _ in range(K)]
             ev_y = [torch.cuda.Event() for _ in range(K)]
 
+            # the device part of a slot (broadcast over NVLink, sharded CsrMV with its carry exchange, copy into
+            # the slot's y buffer) is captured once per slot: the host then issues one graph launch per step
+            def device_part(sl):
+                dist.broadcast(xds[sl], src=0)
+                yds[sl].copy_(op(xds[sl]))
+
+            slot_graphs = []
+            if use_graph:
+                with torch.cuda.stream(s_comp):
+                    for sl in range(K):
+                        device_part(sl)  # warm-up outside capture
+                s_comp.synchronize()
+                for sl in range(K):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=s_comp):
+                        device_part(sl)
+                    slot_graphs.append(g)
+
             def run_pipelined(n):
                 for i in range(n):
                     sl = i % K
@@ -545,8 +563,10 @@ def main():
                         s_comp.wait_event(ev_x[sl])
                         if i >= K:
                             s_comp.wait_event(ev_y[sl])  # the copy that drained this y slot is done
-                        dist.broadcast(xds[sl], src=0)   # NVLink, ordered on the compute stream
-                        yds[sl].copy_(op(xds[sl]))
+                        if slot_graphs:
+                            slot_graphs[sl].replay()
+                        else:
+                            device_part(sl)
                         ev_k[sl].record(s_comp)
                     with torch.cuda.stream(s_d2h):
                         s_d2h.wait_event(ev_k[sl])

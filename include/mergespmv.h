@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define MSPMV_VERSION_MAJOR 0
-#define MSPMV_VERSION_MINOR 1
+#define MSPMV_VERSION_MINOR 2
 
 /* cudaStream_t is passed as void* so that this header needs no CUDA headers. */
 typedef void* mspmv_stream_t;
@@ -170,7 +170,35 @@ int mspmv_host_alloc(void** out, size_t bytes);
 int mspmv_host_free(void* p);
 
 /* -------------------------------------------------------------------------------------------
- * 5. Introspection.
+ * 5. Multi-GPU host-buffer operator: sections 3 and 4 combined behind one handle -- ONE process,
+ *    num_shards GPUs with peer access (NVLink / NVSwitch), no NCCL, no Python (csrc/mg_session.cu).
+ *    New surface: the reference is single-GPU.  create() cuts the CSR into merge-path shards
+ *    (mspmv_shard_partition, cpu_spmv.cpp:311-321 with p = num_shards) and uploads shard g to
+ *    device_ids[g] (NULL: devices 0..num_shards-1; a device may hold several shards).  apply():
+ *    x host -> shard 0's device (one PCIe crossing) -> peer copies to the other devices; every
+ *    device runs mspmv_csrmv_* on its shard plus ONE exchange kernel (mspmv_exchange_carries_*);
+ *    every device copies the rows it owns into their place in y_host.  apply_many() pipelines
+ *    n right-hand sides over three slots and three streams per device like
+ *    mspmv_session_apply_many.  Host buffers should be pinned (mspmv_host_alloc).
+ * ----------------------------------------------------------------------------------------- */
+typedef struct mspmv_mg_session mspmv_mg_session;
+
+int mspmv_mg_session_create(mspmv_mg_session** out, int num_shards, const int* device_ids,
+                            int value_bytes, int num_rows, int num_cols, int num_nonzeros,
+                            const int* row_offsets, const int* column_indices, const void* values);
+int mspmv_mg_session_apply(mspmv_mg_session* s, const void* x_host, void* y_host);
+int mspmv_mg_session_apply_many(mspmv_mg_session* s, int n, const void* xs_host, void* ys_host);
+/* Device-side time of one sharded product (CsrMV + carry exchange on every device, x of the last
+ * apply already resident): `iterations` back-to-back products between two events per device,
+ * the maximum over devices divided by iterations is written to *ms_per_step. */
+int mspmv_mg_session_time_device(mspmv_mg_session* s, int iterations, float* ms_per_step);
+/* Shard g's cut: out[0..3] = (x0, y0, x1, y1) -- rows [x0, x1) end in it, nonzeros [y0, y1) --
+ * and out[4] = its device. */
+int mspmv_mg_session_shard(const mspmv_mg_session* s, int shard, int* out);
+void mspmv_mg_session_destroy(mspmv_mg_session* s);
+
+/* -------------------------------------------------------------------------------------------
+ * 6. Introspection.
  * ----------------------------------------------------------------------------------------- */
 int mspmv_version(void); /* major*100 + minor */
 /* PTX/SASS version the kernels were compiled for, in cub::PtxVersion units (util_device.cuh:118-160:

@@ -11,11 +11,11 @@ CUDA reports an error.
 """
 from . import _lib
 from ._lib import MergeSpmvError, lib, lib_path
-from .csrmv import DeviceSpmv, SpmvSession, csrmv, merge_path_search, swath_coords
+from .csrmv import DeviceSpmv, MultiGpuSpmvSession, SpmvSession, csrmv, temp_storage, merge_path_search, swath_coords
 from . import generators
 from . import sharded
 
 __all__ = [
-    "DeviceSpmv", "SpmvSession", "csrmv", "merge_path_search", "swath_coords", "generators",
+    "DeviceSpmv", "SpmvSession", "MultiGpuSpmvSession", "temp_storage", "csrmv", "merge_path_search", "swath_coords", "generators",
     "sharded", "lib", "lib_path", "MergeSpmvError",
 ]

@@ -28,6 +28,12 @@ SIGNATURES = {
     "mspmv_session_apply": (_i, [_vp, _vp, _vp]),
     "mspmv_session_apply_many": (_i, [_vp, _i, _vp, _vp]),
     "mspmv_session_destroy": (None, [_vp]),
+    "mspmv_mg_session_create": (_i, [C.POINTER(_vp), _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mspmv_mg_session_apply": (_i, [_vp, _vp, _vp]),
+    "mspmv_mg_session_apply_many": (_i, [_vp, _i, _vp, _vp]),
+    "mspmv_mg_session_time_device": (_i, [_vp, _i, C.POINTER(C.c_float)]),
+    "mspmv_mg_session_shard": (_i, [_vp, _i, _vp]),
+    "mspmv_mg_session_destroy": (None, [_vp]),
     "mspmv_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "mspmv_host_free": (_i, [_vp]),
     "mspmv_version": (_i, []),

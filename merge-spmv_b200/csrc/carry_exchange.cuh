@@ -18,6 +18,7 @@
 // requirement and no deadlock as long as every rank eventually launches the kernel.
 #pragma once
 
+#include <stdio.h>
 #include <string.h>
 
 #include "merge_common.cuh"
@@ -25,6 +26,7 @@
 namespace mspmv {
 
 constexpr int kExchangePhasePush = 1, kExchangePhaseFold = 2;
+constexpr uint64_t kExchangeTimeoutNs = 10ull * 1000 * 1000 * 1000;  // 10 s
 
 template <typename T>
 __global__ void carry_exchange_kernel(T* __restrict__ y_local, int carry_index, int y_row_begin, int y_rows,
@@ -49,8 +51,17 @@ __global__ void carry_exchange_kernel(T* __restrict__ y_local, int carry_index, 
         }
     }
     if (phase & kExchangePhaseFold) {
+        // A peer that never launches its kernel (an exception on one rank, mismatched call counts) must not
+        // hang this GPU forever: after kExchangeTimeoutNs the kernel reports and traps, and the host sees a
+        // launch failure at its next synchronisation instead of a silent hang.
+        const uint64_t t_start = global_timer_ns();
         for (int g = threadIdx.x; g < world; g += blockDim.x)
             while (ld_acquire_sys_u64(mine + 2 * world + par * world + g) != epoch) {
+                if (global_timer_ns() - t_start > kExchangeTimeoutNs) {
+                    printf("mspmv carry exchange: rank %d timed out waiting for rank %d (epoch %llu)\n", rank, g,
+                           (unsigned long long)epoch);
+                    trap_kernel();
+                }
             }
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -473,6 +473,7 @@ void mspmv_shard_partition(const int* row_offsets, int num_rows, int num_nonzero
                            int* coords)
 {
     // cpu_spmv.cpp:311-321 with p = num_shards
+    if (num_shards < 1 || !coords || !row_offsets) return;
     int64_t total = (int64_t)num_rows + num_nonzeros;
     int64_t share = (total + num_shards - 1) / num_shards;
     for (int g = 0; g <= num_shards; ++g) {

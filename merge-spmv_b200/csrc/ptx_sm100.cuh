@@ -138,6 +138,15 @@ __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p)
     return v;
 }
 
+// nanosecond wall clock shared by all SMs (bounded spin-waits), and a loud exit
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trap_kernel() { asm volatile("trap;"); }
+
 // L2 prefetch of `bytes` (multiple of 16) at a 16-byte-aligned global address (SASS UBLKPF.L2)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
 {

@@ -239,3 +239,58 @@ class SpmvSession:
             self.close()
         except Exception:
             pass
+
+
+class MultiGpuSpmvSession:
+    """Host-buffer operator over several GPUs of ONE process (``mspmv_mg_session_*``, csrc/mg_session.cu):
+    merge-path shards, peer copies of x, one NVLink carry-exchange kernel per device -- no NCCL, no
+    torch.distributed.  ``devices``: the device of every shard (a device may appear more than once)."""
+
+    def __init__(self, row_offsets, column_indices, values, num_cols, devices):
+        ro = np.ascontiguousarray(row_offsets, dtype=np.int32)
+        ci = np.ascontiguousarray(column_indices, dtype=np.int32)
+        va = np.ascontiguousarray(values)
+        if va.dtype not in (np.float32, np.float64):
+            raise TypeError("ValueT must be float32 or float64")
+        self.dtype = va.dtype
+        self.rows, self.cols, self.nnz = ro.size - 1, int(num_cols), va.size
+        self.devices = [int(d) for d in devices]
+        ids = (C.c_int * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().mspmv_mg_session_create(
+            C.byref(self._h), len(self.devices), ids, va.dtype.itemsize, self.rows, self.cols, self.nnz,
+            ro.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), va.ctypes.data_as(C.c_void_p)),
+            "mg_session_create")
+
+    _host_ptr = staticmethod(SpmvSession._host_ptr)
+
+    def apply(self, x_host, y_host):
+        _lib.check(_lib.lib().mspmv_mg_session_apply(self._h, self._host_ptr(x_host), self._host_ptr(y_host)),
+                   "mg_session_apply")
+        return y_host
+
+    def apply_many(self, n, xs_host, ys_host):
+        _lib.check(_lib.lib().mspmv_mg_session_apply_many(self._h, int(n), self._host_ptr(xs_host),
+                                                          self._host_ptr(ys_host)), "mg_session_apply_many")
+        return ys_host
+
+    def time_device(self, iterations):
+        ms = C.c_float()
+        _lib.check(_lib.lib().mspmv_mg_session_time_device(self._h, int(iterations), C.byref(ms)), "mg_session_time_device")
+        return float(ms.value)
+
+    def shard(self, g):
+        out = (C.c_int * 5)()
+        _lib.check(_lib.lib().mspmv_mg_session_shard(self._h, int(g), out), "mg_session_shard")
+        return dict(x0=out[0], y0=out[1], x1=out[2], y1=out[3], device=out[4])
+
+    def close(self):
+        if self._h:
+            _lib.lib().mspmv_mg_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

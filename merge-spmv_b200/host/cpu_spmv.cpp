@@ -11,6 +11,7 @@
 using namespace mspmv_host;
 
 static bool g_quiet = false;
+static bool g_verbose2 = false;  // --v2: display the input matrix (cpu_spmv.cpp:74,604,722); --v is parsed and unused there (:73,721)
 static int g_omp_threads = -1;
 
 static inline void merge_path_search(int diagonal, const int* row_end_offsets, int a_len, int b_len, int& x, int& y)
@@ -80,7 +81,9 @@ static void run_tests(const CommandLineArgs& args, V alpha, V beta, int timing_i
     if (!g_quiet) {
         std::printf("\n");
         display_histogram(a);
-        std::printf("\n\n");
+        std::printf("\n");
+        if (g_verbose2) display_matrix(a);
+        std::printf("\n");
     }
     std::fflush(stdout);
     if (timing_iterations == -1) {  // cpu_spmv.cpp:609-615: printed after the statistics, only when adaptive
@@ -128,6 +131,8 @@ int main(int argc, char** argv)
     int timing_iterations = -1;
     float alpha = 1.0f, beta = 0.0f;
     g_quiet = args.CheckCmdLineFlag("quiet");
+    (void)args.CheckCmdLineFlag("v");
+    g_verbose2 = args.CheckCmdLineFlag("v2");
     const bool fp32 = args.CheckCmdLineFlag("fp32");
     args.GetCmdLineArgument("i", timing_iterations);
     args.GetCmdLineArgument("threads", g_omp_threads);

@@ -10,6 +10,8 @@
 // by the merge kernel (the reference's ignores them and would print FAIL); new synthetic
 // families --uniform/--powerlaw/--banded; a line with the algorithmic-bytes roofline fraction.
 #include <cuda_runtime.h>
+
+#include <chrono>
 #include <cusparse.h>
 
 #include "../../include/mergespmv_cub_shim.hpp"
@@ -18,6 +20,8 @@
 using namespace mspmv_host;
 
 static bool g_quiet = false;
+static bool g_verbose = false;   // --v: display the reference and computed vectors (gpu_spmv.cu:59,711; utils.h:785-798)
+static bool g_verbose2 = false;  // --v2: display the input matrix (gpu_spmv.cu:60,510,712)
 
 #define CUDA_EXIT(e)                                                                              \
     do {                                                                                          \
@@ -28,6 +32,13 @@ static bool g_quiet = false;
             std::exit(1);                                                                         \
         }                                                                                         \
     } while (0)
+
+struct WallTimer {  // host wall clock (utils.h:528-553 uses omp_get_wtime for the same purpose)
+    std::chrono::steady_clock::time_point a, b;
+    void Start() { a = std::chrono::steady_clock::now(); }
+    void Stop() { b = std::chrono::steady_clock::now(); }
+    float ElapsedMillis() const { return std::chrono::duration<float, std::milli>(b - a).count(); }
+};
 
 struct GpuTimer {  // utils.h:624-658
     cudaEvent_t start, stop;
@@ -63,6 +74,13 @@ static int compare_device(const V* h_reference, const V* d_data, int n)  // util
 {
     std::vector<V> h(n);
     CUDA_EXIT(cudaMemcpy(h.data(), d_data, sizeof(V) * n, cudaMemcpyDeviceToHost));
+    if (g_verbose) {  // display_data of CompareDeviceResults (utils.h:785-798)
+        std::printf("Reference:\n");
+        for (int i = 0; i < n; ++i) std::printf("%g, ", (double)h_reference[i]);
+        std::printf("\n\nComputed:\n");
+        for (int i = 0; i < n; ++i) std::printf("%g, ", (double)h[i]);
+        std::printf("\n\n");
+    }
     return compare_results(h.data(), h_reference, n, true);
 }
 
@@ -189,159 +207,52 @@ static float test_toolkit_cub(const Csr<V>& a, const V* y_in, const V* y_ref, De
 }
 
 // ---- one process, several GPUs (new surface: the reference is single-GPU, README.md:5) ---------
-// The matrix is cut into merge-path shards exactly like OmpMergeCsrmv cuts it between CPU threads
-// (cpu_spmv.cpp:311-321, mspmv_shard_partition); device g runs the unchanged single-GPU CsrMV on its
-// shard and then the NVLink carry exchange (mspmv_exchange_carries_*): it stores its carry into every
-// peer's exchange buffer -- plain cudaMalloc memory, peer access enabled, no NCCL -- waits for the
-// peers' flags and folds.  Launches are asynchronous, so one host thread can drive all devices; nothing
-// here blocks on a device before every device has been given its exchange kernel.
-static int csrmv_any(void* t, size_t* b, const double* v, const int* ro, const int* ci, const double* x, double* y, int r,
-                     int c, int n, cudaStream_t s)
-{
-    return mspmv_csrmv_f64(t, b, v, ro, ci, x, y, r, c, n, s, 0);
-}
-static int csrmv_any(void* t, size_t* b, const float* v, const int* ro, const int* ci, const float* x, float* y, int r,
-                     int c, int n, cudaStream_t s)
-{
-    return mspmv_csrmv_f32(t, b, v, ro, ci, x, y, r, c, n, s, 0);
-}
-static int exchange_any(double* y, int lr, int b, int n, int rg, const int* cr, void* const* pb, int rank, int p,
-                        unsigned long long* e, cudaStream_t s)
-{
-    return mspmv_exchange_carries_f64(y, lr, b, n, rg, cr, pb, rank, p, e, s);
-}
-static int exchange_any(float* y, int lr, int b, int n, int rg, const int* cr, void* const* pb, int rank, int p,
-                        unsigned long long* e, cudaStream_t s)
-{
-    return mspmv_exchange_carries_f32(y, lr, b, n, rg, cr, pb, rank, p, e, s);
-}
-
+// mspmv_mg_session_* (include/mergespmv.h section 5): the matrix is cut into merge-path shards exactly
+// like OmpMergeCsrmv cuts it between CPU threads (cpu_spmv.cpp:311-321); device g runs the unchanged
+// single-GPU CsrMV on its shard and then the NVLink carry-exchange kernel -- no NCCL.  The driver keeps
+// the reference's protocol: one warm-up product checked against SpmvGold, then `timing_iterations`
+// device-timed products (x resident), max over devices.
 template <typename V>
 static float test_merge_csrmv_multi(const Csr<V>& a, const V* x_host, const V* y_ref, int p, int timing_iterations,
                                     float& setup_ms)
 {
-    struct Dev {
-        cudaStream_t stream = nullptr;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        V *val = nullptr, *x = nullptr, *y = nullptr;
-        int *ro = nullptr, *col = nullptr, *carry_rows = nullptr;
-        void *temp = nullptr, *xbuf = nullptr;
-        void** peers = nullptr;
-        unsigned long long* epoch = nullptr;
-        size_t temp_bytes = 0;
-        int x0 = 0, y0 = 0, x1 = 0, y1 = 0, local_rows = 0, owned = 0, nnz = 0;
-    };
-    std::vector<Dev> d(p);
-    std::vector<int> coords(2 * (p + 1));
-    mspmv_shard_partition(a.row_offsets.data(), a.num_rows, a.num_nonzeros, p, coords.data());
-    std::vector<int> carry_rows(p);
-    for (int g = 0; g < p; ++g) carry_rows[g] = coords[2 * (g + 1)];
-    const size_t xbytes = mspmv_exchange_buffer_bytes(p);
-    GpuTimer setup;
-    CUDA_EXIT(cudaSetDevice(0));
+    mspmv_mg_session* s = nullptr;
+    WallTimer setup;
     setup.Start();
-    for (int g = 0; g < p; ++g) {
-        Dev& D = d[g];
-        CUDA_EXIT(cudaSetDevice(g));
-        for (int h = 0; h < p; ++h) {
-            if (h == g) continue;
-            cudaError_t e = cudaDeviceEnablePeerAccess(h, 0);
-            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-            else CUDA_EXIT(e);
-        }
-        CUDA_EXIT(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
-        CUDA_EXIT(cudaEventCreate(&D.e0));
-        CUDA_EXIT(cudaEventCreate(&D.e1));
-        D.x0 = coords[2 * g], D.y0 = coords[2 * g + 1], D.x1 = coords[2 * g + 2], D.y1 = coords[2 * g + 3];
-        D.owned = D.x1 - D.x0, D.local_rows = D.owned + 1, D.nnz = D.y1 - D.y0;
-        std::vector<int> lro(D.local_rows + 1);
-        mspmv_shard_row_offsets(a.row_offsets.data(), D.x0, D.y0, D.x1, D.y1, lro.data());
-        CUDA_EXIT(cudaMalloc(&D.val, sizeof(V) * std::max(D.nnz, 1)));
-        CUDA_EXIT(cudaMalloc(&D.col, sizeof(int) * std::max(D.nnz, 1)));
-        CUDA_EXIT(cudaMalloc(&D.ro, sizeof(int) * (D.local_rows + 1)));
-        CUDA_EXIT(cudaMalloc(&D.x, sizeof(V) * a.num_cols));
-        CUDA_EXIT(cudaMalloc(&D.y, sizeof(V) * D.local_rows));
-        CUDA_EXIT(cudaMalloc(&D.carry_rows, sizeof(int) * p));
-        CUDA_EXIT(cudaMalloc(&D.xbuf, xbytes));
-        CUDA_EXIT(cudaMalloc(&D.peers, sizeof(void*) * p));
-        CUDA_EXIT(cudaMalloc(&D.epoch, sizeof(unsigned long long)));
-        CUDA_EXIT(cudaMemset(D.xbuf, 0, xbytes));
-        CUDA_EXIT(cudaMemset(D.epoch, 0, sizeof(unsigned long long)));
-        CUDA_EXIT(cudaMemcpy(D.val, a.values.data() + D.y0, sizeof(V) * D.nnz, cudaMemcpyHostToDevice));
-        CUDA_EXIT(cudaMemcpy(D.col, a.column_indices.data() + D.y0, sizeof(int) * D.nnz, cudaMemcpyHostToDevice));
-        CUDA_EXIT(cudaMemcpy(D.ro, lro.data(), sizeof(int) * (D.local_rows + 1), cudaMemcpyHostToDevice));
-        CUDA_EXIT(cudaMemcpy(D.x, x_host, sizeof(V) * a.num_cols, cudaMemcpyHostToDevice));
-        CUDA_EXIT(cudaMemcpy(D.carry_rows, carry_rows.data(), sizeof(int) * p, cudaMemcpyHostToDevice));
-        CUDA_EXIT((cudaError_t)csrmv_any(nullptr, &D.temp_bytes, (const V*)nullptr, nullptr, nullptr, (const V*)nullptr,
-                                         (V*)nullptr, D.local_rows, a.num_cols, D.nnz, nullptr));
-        CUDA_EXIT(cudaMalloc(&D.temp, D.temp_bytes));
-    }
-    std::vector<void*> table(p);
-    for (int g = 0; g < p; ++g) table[g] = d[g].xbuf;
-    for (int g = 0; g < p; ++g) {
-        CUDA_EXIT(cudaSetDevice(g));
-        CUDA_EXIT(cudaMemcpy(d[g].peers, table.data(), sizeof(void*) * p, cudaMemcpyHostToDevice));
-        CUDA_EXIT(cudaDeviceSynchronize());
-    }
-    CUDA_EXIT(cudaSetDevice(0));
+    CUDA_EXIT((cudaError_t)mspmv_mg_session_create(&s, p, nullptr, (int)sizeof(V), a.num_rows, a.num_cols, a.num_nonzeros,
+                                                   a.row_offsets.data(), a.column_indices.data(), a.values.data()));
     setup.Stop();
     setup_ms = setup.ElapsedMillis();
-
-    auto step = [&] {
-        for (int g = 0; g < p; ++g) {
-            Dev& D = d[g];
-            CUDA_EXIT(cudaSetDevice(g));
-            CUDA_EXIT((cudaError_t)csrmv_any(D.temp, &D.temp_bytes, D.val, D.ro, D.col, D.x, D.y, D.local_rows, a.num_cols,
-                                             D.nnz, D.stream));
-            CUDA_EXIT((cudaError_t)exchange_any(D.y, D.local_rows, D.x0, D.owned, a.num_rows, D.carry_rows, D.peers, g, p,
-                                                D.epoch, D.stream));
-        }
-    };
-    auto sync_all = [&] {
-        for (int g = 0; g < p; ++g) {
-            CUDA_EXIT(cudaSetDevice(g));
-            CUDA_EXIT(cudaStreamSynchronize(d[g].stream));
-        }
-    };
-    step();  // warm-up + check
-    sync_all();
+    V *xh = nullptr, *yh = nullptr;
+    CUDA_EXIT((cudaError_t)mspmv_host_alloc((void**)&xh, sizeof(V) * (size_t)a.num_cols));
+    CUDA_EXIT((cudaError_t)mspmv_host_alloc((void**)&yh, sizeof(V) * (size_t)a.num_rows));
+    std::memcpy(xh, x_host, sizeof(V) * (size_t)a.num_cols);
+    CUDA_EXIT((cudaError_t)mspmv_mg_session_apply(s, xh, yh));  // warm-up + check
     if (!g_quiet) {
-        std::vector<V> y(a.num_rows);
-        for (int g = 0; g < p; ++g) {
-            CUDA_EXIT(cudaSetDevice(g));
-            if (d[g].owned > 0)
-                CUDA_EXIT(cudaMemcpy(y.data() + d[g].x0, d[g].y, sizeof(V) * d[g].owned, cudaMemcpyDeviceToHost));
-        }
-        int compare = compare_results(y.data(), y_ref, a.num_rows, true);
+        int compare = compare_results(yh, y_ref, a.num_rows, true);
         std::printf("\t%s\n", compare ? "FAIL" : "PASS");
         std::fflush(stdout);
     }
-    for (int g = 0; g < p; ++g) {
-        CUDA_EXIT(cudaSetDevice(g));
-        CUDA_EXIT(cudaEventRecord(d[g].e0, d[g].stream));
-    }
-    for (int it = 0; it < timing_iterations; ++it) step();
-    float elapsed = 0.f;
-    for (int g = 0; g < p; ++g) {
-        CUDA_EXIT(cudaSetDevice(g));
-        CUDA_EXIT(cudaEventRecord(d[g].e1, d[g].stream));
-    }
-    for (int g = 0; g < p; ++g) {  // device-side time, max over devices
-        CUDA_EXIT(cudaSetDevice(g));
-        CUDA_EXIT(cudaEventSynchronize(d[g].e1));
-        float ms = 0.f;
-        CUDA_EXIT(cudaEventElapsedTime(&ms, d[g].e0, d[g].e1));
-        elapsed = std::max(elapsed, ms);
-    }
-    for (int g = 0; g < p; ++g) {
-        Dev& D = d[g];
-        CUDA_EXIT(cudaSetDevice(g));
-        cudaFree(D.val), cudaFree(D.col), cudaFree(D.ro), cudaFree(D.x), cudaFree(D.y), cudaFree(D.carry_rows);
-        cudaFree(D.xbuf), cudaFree(D.peers), cudaFree(D.epoch), cudaFree(D.temp);
-        cudaEventDestroy(D.e0), cudaEventDestroy(D.e1), cudaStreamDestroy(D.stream);
-    }
-    CUDA_EXIT(cudaSetDevice(0));
-    return elapsed / timing_iterations;
+    float ms = 0.f;
+    CUDA_EXIT((cudaError_t)mspmv_mg_session_time_device(s, timing_iterations, &ms));
+    // end to end with host buffers: 3-slot pipeline over the same x (what a solver's host loop would see)
+    const int n_e2e = 24;
+    V *xs = nullptr, *ys = nullptr;
+    CUDA_EXIT((cudaError_t)mspmv_host_alloc((void**)&xs, sizeof(V) * (size_t)a.num_cols * n_e2e));
+    CUDA_EXIT((cudaError_t)mspmv_host_alloc((void**)&ys, sizeof(V) * (size_t)a.num_rows * n_e2e));
+    for (int i = 0; i < n_e2e; ++i) std::memcpy(xs + (size_t)i * a.num_cols, x_host, sizeof(V) * (size_t)a.num_cols);
+    CUDA_EXIT((cudaError_t)mspmv_mg_session_apply_many(s, 3, xs, ys));
+    WallTimer e2e;
+    e2e.Start();
+    CUDA_EXIT((cudaError_t)mspmv_mg_session_apply_many(s, n_e2e, xs, ys));
+    e2e.Stop();
+    if (!g_quiet)
+        std::printf("\thost buffers, pipelined (mspmv_mg_session_apply_many): %.4f ms per product, %.2f gflops%s\n",
+                    e2e.ElapsedMillis() / n_e2e, 2.0 * a.num_nonzeros / (e2e.ElapsedMillis() / n_e2e) / 1e6,
+                    std::memcmp(ys + (size_t)(n_e2e - 1) * a.num_rows, yh, sizeof(V) * (size_t)a.num_rows) ? "  MISMATCH" : "");
+    mspmv_host_free(xs), mspmv_host_free(ys), mspmv_host_free(xh), mspmv_host_free(yh);
+    mspmv_mg_session_destroy(s);
+    return ms;
 }
 
 template <typename V>
@@ -378,7 +289,9 @@ static void run_tests(const CommandLineArgs& args, V alpha, V beta, int timing_i
     if (!g_quiet) {
         std::printf("\n");
         display_histogram(a);
-        std::printf("\n\n");
+        std::printf("\n");
+        if (g_verbose2) display_matrix(a);
+        std::printf("\n");
     }
     std::fflush(stdout);
 
@@ -465,6 +378,8 @@ int main(int argc, char** argv)
     int timing_iterations = -1, dev = 0;
     float alpha = 1.0f, beta = 0.0f;
     g_quiet = args.CheckCmdLineFlag("quiet");
+    g_verbose = args.CheckCmdLineFlag("v");
+    g_verbose2 = args.CheckCmdLineFlag("v2");
     const bool fp32 = args.CheckCmdLineFlag("fp32");
     args.GetCmdLineArgument("i", timing_iterations);
     args.GetCmdLineArgument("alpha", alpha);

@@ -459,6 +459,20 @@ void spmv_gold(const Csr<V>& a, const V* x, const V* y_in, V* y_out, V alpha, V 
     }
 }
 
+// CsrMatrix::Display (sparse_matrix.h:962-975): the --v2 dump of the input matrix
+template <typename V>
+void display_matrix(const Csr<V>& m)
+{
+    std::printf("Input Matrix (%d vertices, %d nonzeros):\n", m.num_rows, m.num_nonzeros);
+    for (int row = 0; row < m.num_rows; ++row) {
+        std::printf("%d [@%d, #%d]: ", row, m.row_offsets[row], m.row_offsets[row + 1] - m.row_offsets[row]);
+        for (int k = m.row_offsets[row]; k < m.row_offsets[row + 1]; ++k)
+            std::printf("%d (%f), ", m.column_indices[k], (double)m.values[k]);
+        std::printf("\n");
+    }
+    std::fflush(stdout);
+}
+
 template <typename V>
 int compare_results(const V* computed, const V* reference, int len, bool verbose = true)
 {

@@ -118,6 +118,12 @@ inline void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
     if (((uintptr_t)src_gmem & 15) || (bytes & 15) || bytes == 0)
         emu::die("cp.async.bulk.prefetch: address must be 16-byte aligned and the size a non-zero multiple of 16");
 }
+inline uint64_t global_timer_ns()
+{
+    static uint64_t t = 0;
+    return t += 1000;  // a microsecond per look at the clock: the 10 s limit is ~10 million polls
+}
+inline void trap_kernel() { emu::die("kernel trapped"); }
 inline void st_relaxed_sys_u64(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 inline void st_release_sys_u64(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 EMU_INTERNAL inline uint64_t ld_acquire_sys_u64(const uint64_t* p)

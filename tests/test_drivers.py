@@ -148,6 +148,15 @@ def test_human_output_matches_reference_driver(ref):
     assert any(l.strip() == "PASS" for l in ours)
 
 
+def test_v2_matrix_display_matches_reference_driver(ref):
+    """--v2 prints the input matrix (cpu_spmv.cpp:604 -> CsrMatrix::Display, sparse_matrix.h:962-975):
+    the same lines as the reference's own main(), character for character."""
+    flags = ["--grid2d=4", "--i=1", "--v2", "--threads=1"]
+    grab = lambda ls: [l for l in ls if l.startswith("Input Matrix") or " [@" in l]
+    theirs, ours = grab(_reference_driver_stdout(flags).splitlines()), grab(run([CPU] + flags).stdout.splitlines())
+    assert ours == theirs and len(ours) == 17
+
+
 def test_cpu_driver_pass_and_threads():
     r = run([CPU, "--grid3d=30", "--i=5", "--threads=3"])
     assert r.returncode == 0 and "PASS" in r.stdout and "Using 3 threads" in r.stdout
@@ -166,6 +175,14 @@ def test_gpu_driver_self_check():
         assert r.returncode == 0, r.stderr
         assert "FAIL" not in r.stdout and r.stdout.count("PASS") >= 1, r.stdout
         assert "Merge-based CsrMV" in r.stdout and "effective GB/s" in r.stdout
+    # --v: reference and computed vectors (utils.h:785-798); --v2: the input matrix; --gpus: the multi-GPU session
+    r = run([GPU, "--grid2d=5", "--i=2", "--v", "--v2"])
+    assert "Reference:" in r.stdout and "Computed:" in r.stdout and "Input Matrix (25 vertices, 80 nonzeros):" in r.stdout
+    import torch
+    n = torch.cuda.device_count()
+    if n >= 2:
+        r = run([GPU, "--uniform=64", f"--rows={65536 * n}", "--cols=65536", "--values=random", "--randx", "--i=20", f"--gpus={n}"])
+        assert r.returncode == 0 and "FAIL" not in r.stdout and r.stdout.count("PASS") == 2 and "MISMATCH" not in r.stdout, r.stdout
     r = run([GPU, "--grid2d=300", "--quiet", "--i=10"])
     fields = [f.strip() for f in r.stdout.strip().rstrip(",").split(",")]
     # label, 7 stats, device, fp64, method, 4 perf numbers (gpu_spmv.cu:532-534,467-471)

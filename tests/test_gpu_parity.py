@@ -393,3 +393,43 @@ def test_launch_counter_and_config():
     before = L.mspmv_launch_count()
     ms.csrmv(m.row_offsets, m.col, m.val, x)
     assert L.mspmv_launch_count() - before == csrmv_config(8, m.rows, m.nnz)["kernels_per_call"] == 2
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("layout", ["one_device_3_shards", "all_devices"])
+def test_mg_session_c_abi(orc, dt, layout):
+    """mspmv_mg_session_* (one process, several shards, NVLink carry-exchange kernel, no NCCL): on a single
+    GPU the shards share the device (same kernels, same exchange protocol through same-device pointers); with
+    more GPUs every device gets one shard.  Against the oracle with p = shards threads -- the same
+    decomposition -- and bit-exact on all-ones inputs; apply_many == apply bit for bit."""
+    ndev = torch.cuda.device_count()
+    devices = [0, 0, 0] if layout == "one_device_3_shards" else list(range(ndev))
+    if layout == "all_devices" and ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    m = gen.make_config("powerlaw_2m", scale=1 / 64, values="random", dtype=torch.float64)
+    ro, col, val = m.numpy()
+    val = val.astype(dt)
+    tdt = torch.from_numpy(val).dtype
+    sess = ms.MultiGpuSpmvSession(ro, col, val, m.cols, devices)
+    cuts = [sess.shard(g) for g in range(len(devices))]
+    assert cuts[0]["x0"] == 0 and cuts[-1]["x1"] == m.rows and cuts[-1]["y1"] == m.nnz
+    assert [c["device"] for c in cuts] == devices
+    n = 5
+    xs = torch.empty((n, m.cols), dtype=tdt).pin_memory()
+    ys = torch.full((n, m.rows), float("nan"), dtype=tdt).pin_memory()
+    for i in range(n):
+        xs[i] = gen.vector(m.cols, tdt, "random", seed=300 + i)
+    y0 = torch.full((m.rows,), float("nan"), dtype=tdt).pin_memory()
+    sess.apply(xs[0], y0)
+    assert_close(y0.numpy(), orc.merge_csrmv(ro, col, val, xs[0].numpy(), len(devices)), ro, dt, "mg apply")
+    sess.apply_many(n, xs, ys)
+    assert np.array_equal(ys[0].numpy(), y0.numpy())
+    for i in range(n):
+        assert_close(ys[i].numpy(), orc.merge_csrmv(ro, col, val, xs[i].numpy(), len(devices)), ro, dt, f"mg apply_many {i}")
+    assert sess.time_device(3) > 0
+    sess.close()
+    ones = ms.MultiGpuSpmvSession(ro, col, np.ones_like(val), m.cols, devices)
+    y1 = torch.full((m.rows,), float("nan"), dtype=tdt).pin_memory()
+    ones.apply(torch.ones(m.cols, dtype=tdt).pin_memory(), y1)
+    assert np.array_equal(y1.numpy(), np.diff(ro).astype(dt))
+    ones.close()
