@@ -9,6 +9,8 @@ PY=python
 TR="$PY -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 echo "== $N GPUs: NCCL parity tests (incl. the opt-in p2p exchange and graph capture of the y exchange)" | tee -a "$LOG"
 MSPMV_TEST_EXPERIMENTAL=1 timeout 900 $PY -m pytest tests/test_multi_gpu.py -m gpu -q -x 2>&1 | tail -4 | tee -a "$LOG"
+echo "== C-ABI multi-GPU session + C++ driver tests on $N devices" | tee -a "$LOG"
+timeout 900 $PY -m pytest tests -m gpu -q -x -k "mg_session or gpu_driver_self_check" 2>&1 | tail -4 | tee -a "$LOG"
 summ() { $PY -c "
 import json,sys
 d=json.loads(sys.argv[1])
@@ -33,5 +35,5 @@ echo "== reference arm under torchrun (rank 0 only)" | tee -a "$LOG"
 timeout 900 $TR --master-port 29521 bench.py --impl reference --gpus $N --steps 5 --warmup 3 2>/dev/null | tail -1 | cut -c1-600 | tee -a "$LOG"
 echo "== C++ driver, one process driving $N devices (peer-memory carry exchange, no NCCL, no Python)" | tee -a "$LOG"
 timeout 900 merge-spmv_b200/gpu_spmv --uniform=64 --rows=$((1048576 * N)) --cols=1048576 --values=random --randx --gpus=$N 2>&1 \
-    | grep -E "CsrMV|PASS|FAIL|avg ms|rror" | tee -a "$LOG"
+    | grep -E "CsrMV|PASS|FAIL|avg ms|rror|host buffers" | tee -a "$LOG"
 echo done | tee -a "$LOG"
