@@ -301,9 +301,13 @@ def main():
                     help="replay each step (3 kernels, plus the collective and carry fold at N>1) as one CUDA graph; auto = on")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="mspmv_set_option before the run (e.g. pipe_config=2, pipe_search=0); recorded in config.options")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
-                    help="N>1: how the carries travel -- nccl: one all_gather + fold kernel (default); p2p: one kernel "
-                         "per rank storing into the peers' symmetric memory over NVLink (csrc/carry_exchange.cuh)")
+    ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"],
+                    help="N>1: how the carries travel -- p2p (default): one kernel per rank storing into the peers' "
+                         "symmetric memory over NVLink, fused with the fold (csrc/carry_exchange.cuh; 0.330 vs 0.409 ms "
+                         "per step at 8 GPUs, profiles/mg_sweep_r02_n8.txt); nccl: one all_gather + fold kernel")
+    ap.add_argument("--e2e-broadcast", action="store_true",
+                    help="N>1 end to end: x crosses PCIe once (rank 0) and is broadcast over NVLink by NCCL, instead of "
+                         "every rank uploading its own copy (default)")
     ap.add_argument("--e2e-sequential", action="store_true",
                     help="N>1: run the end-to-end steps one after the other instead of the default three-stream "
                          "pipeline (H2D of x | broadcast + product | D2H of the y slice over three buffer slots)")
@@ -518,12 +522,14 @@ def main():
                    "unpipelined_ms_per_step": single_ms, "matrix_upload_ms": setup_ms,
                    "matrix_upload_bytes": int(nnz * (vb + 4) + (rows + 1) * 4)}
         else:
-            # N > 1.  x arrives in ONE host buffer (rank 0, pinned): it crosses PCIe once and is then
-            # broadcast over NVLink (NCCL) -- not uploaded N times -- and every rank returns its slice of y
-            # to its own pinned host buffer.  Three streams over K slots:  H2D(i+1) | bcast + product(i) | D2H(i-1)
-            # (what mspmv_session_apply_many does at N=1).  --e2e-sequential: one step after the other.
+            # N > 1.  Every rank feeds its GPU from its own pinned host copy of x over its own PCIe link and
+            # returns its slice of y to its own pinned host buffer (--e2e-broadcast: x crosses PCIe once, on rank
+            # 0, and NCCL broadcasts it over NVLink).  Three streams over K slots:
+            #   H2D(i+1) | product + carry exchange (i) | D2H(i-1)      (what mspmv_session_apply_many does at N=1)
+            # --e2e-sequential: one step after the other.
             K = 3
-            xh = x.cpu().pin_memory() if rank == 0 else None
+            bcast = bool(args.e2e_broadcast)
+            xh = x.cpu().pin_memory() if (rank == 0 or not bcast) else None
             s_h2d, s_comp, s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
             xds = [torch.empty_like(x) for _ in range(K)]
             yds = [torch.empty(shard.owned_rows, dtype=dt, device=dev) for _ in range(K)]
@@ -532,14 +538,17 @@ def main():
             ev_k = [torch.cuda.Event() for _ in range(K)]
             ev_y = [torch.cuda.Event() for _ in range(K)]
 
-            # the device part of a slot (broadcast over NVLink, sharded CsrMV with its carry exchange, copy into
-            # the slot's y buffer) is captured once per slot: the host then issues one graph launch per step
+            # the device part of a slot (sharded CsrMV with its carry exchange, copy into the slot's y buffer) is
+            # captured once per slot: the host then issues one graph launch per step.  With the p2p exchange the
+            # graph holds no NCCL work (the NCCL paths -- --exchange nccl, --e2e-broadcast -- stay eager: replaying
+            # graphs that contain collectives next to eager collectives costs milliseconds per switch)
             def device_part(sl):
-                dist.broadcast(xds[sl], src=0)
+                if bcast:
+                    dist.broadcast(xds[sl], src=0)
                 yds[sl].copy_(op(xds[sl]))
 
             slot_graphs = []
-            if use_graph:
+            if use_graph and not bcast and args.exchange == "p2p":
                 with torch.cuda.stream(s_comp):
                     for sl in range(K):
                         device_part(sl)  # warm-up outside capture
@@ -556,7 +565,7 @@ def main():
                     with torch.cuda.stream(s_h2d):
                         if i >= K:
                             s_h2d.wait_event(ev_k[sl])   # the product that read this x slot is done
-                        if rank == 0:
+                        if xh is not None:
                             xds[sl].copy_(xh, non_blocking=True)
                         ev_x[sl].record(s_h2d)
                     with torch.cuda.stream(s_comp):
@@ -577,9 +586,10 @@ def main():
 
             def run_sequential(n):
                 for i in range(n):
-                    if rank == 0:
+                    if xh is not None:
                         xds[0].copy_(xh, non_blocking=True)
-                    dist.broadcast(xds[0], src=0)
+                    if bcast:
+                        dist.broadcast(xds[0], src=0)
                     yhs[0].copy_(op(xds[0]), non_blocking=True)
                 torch.cuda.synchronize()
 
@@ -596,11 +606,13 @@ def main():
             tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e = {"value": 2.0 * nnz * n_e2e / float(tt.item()) / 1e9, "unit": UNIT,
-                   "h2d_bytes_per_step": cols * vb, "d2h_bytes_per_step": rows * vb, "steps": n_e2e,
-                   "api": "ShardedSpmv: pinned host x on rank 0 -> one H2D -> NCCL broadcast over NVLink -> sharded CsrMV "
-                          "-> every rank's y slice D2H to pinned host memory"
+                   "h2d_bytes_per_step": cols * vb * (1 if bcast else world), "d2h_bytes_per_step": rows * vb,
+                   "steps": n_e2e,
+                   "api": ("ShardedSpmv: pinned host x on rank 0 -> one H2D -> NCCL broadcast over NVLink" if bcast else
+                           "ShardedSpmv: every rank uploads x from its own pinned host copy over its own PCIe link")
+                          + " -> sharded CsrMV + carry exchange -> every rank's y slice D2H to pinned host memory"
                           + (", sequential" if args.e2e_sequential else ", three-stream pipeline over 3 slots"),
-                   "bytes_note": "h2d = x once (rank 0); d2h = all ranks' slices together"}
+                   "bytes_note": "totals over all ranks"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------
     cpu = None

@@ -122,10 +122,12 @@ class ShardedSpmv:
     """y_shard = (A x)[x_g : x_{g+1}) on this rank; call collectively on all ranks."""
 
     def __init__(self, shard: Shard, group=None, local_spmv=None, fold=None, exchange="nccl"):
-        """``exchange``: how the p carry values travel.  "nccl" (default): one ``all_gather`` + the fold
-        kernel.  "p2p": ONE kernel per rank that stores its carry straight into every peer's
-        symmetric-memory buffer over NVLink, waits for the peers' flags and folds
-        (``mspmv_exchange_carries_*``, csrc/carry_exchange.cuh) -- no NCCL on the data path."""
+        """``exchange``: how the p carry values travel.  "nccl": one ``all_gather`` + the fold kernel
+        (the portable form, and what the CPU / gloo tests exercise).  "p2p": ONE kernel per rank that
+        stores its carry straight into every peer's symmetric-memory buffer over NVLink, waits for the
+        peers' flags and folds (``mspmv_exchange_carries_*``, csrc/carry_exchange.cuh) -- no NCCL on the
+        data path; measured 0.330 vs 0.409 ms per step at 8 GPUs and a tie at 2
+        (profiles/mg_sweep_r02_n*.txt), so bench.py and anything latency-bound should pass "p2p"."""
         if exchange not in ("nccl", "p2p"):
             raise ValueError("exchange must be 'nccl' or 'p2p'")
         self.shard = shard
