@@ -304,6 +304,7 @@ static int csrmv(void* d_temp, size_t* temp_bytes, const T* values, const int* r
     }
     if (*temp_bytes < p.bytes) return (int)cudaErrorInvalidValue;  // util_device.cuh:90-93
     if (num_rows == 0) return 0;
+    if (!row_offsets || !y || (num_nonzeros > 0 && (!values || !col || !x))) return (int)cudaErrorInvalidValue;
     char* temp = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_temp) + 255) & ~uintptr_t(255));
     return csrmv_launch<T, AXPBY>(p, temp, values, row_offsets, col, x, y, num_rows, num_nonzeros,
                                   alpha, beta, (cudaStream_t)stream_v, debug_sync);
@@ -340,7 +341,8 @@ static int exchange_carries(T* y_local, int local_rows, int y_row_begin, int y_r
                             const int* carry_rows, void* const* peer_bufs, int rank, int num_shards,
                             unsigned long long* epoch, void* stream_v)
 {
-    if (!y_local || !carry_rows || !peer_bufs || !epoch || local_rows < 1 || rank < 0 || rank >= num_shards)
+    if (!y_local || !carry_rows || !peer_bufs || !epoch || local_rows < 1 || num_shards < 1 || rank < 0 ||
+        rank >= num_shards)
         return (int)cudaErrorInvalidValue;
     cudaStream_t stream = (cudaStream_t)stream_v;
     carry_exchange_kernel<T><<<1, 32, 0, stream>>>(y_local, local_rows - 1, y_row_begin, y_rows, num_rows_global,
