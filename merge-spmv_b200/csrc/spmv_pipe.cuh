@@ -45,6 +45,10 @@
 
 namespace mspmv {
 
+#ifndef MSPMV_PIPE_VALS_FIRST
+#define MSPMV_PIPE_VALS_FIRST 1
+#endif
+
 // Compile-time shape of one kernel instantiation.
 //   IPT     nonzero slots per consumer thread (odd: conflict-free strided shared-memory reads)
 //   VST     slots of the value / row-offset ring      CST   slots of the column-index ring
@@ -304,6 +308,19 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
     auto step = [&](int i, T(&xc)[IPT], T(&xn)[IPT]) {
         const int s = i % STAGES, bsel = i & 1;
         PipeStage<C>& st = stages[s];
+        const int x0 = cur.x, y0 = cur.y, nrows = cur.z - cur.x, nnzs = cur.w - cur.y;
+        const int off_v = (y0 + shift_v) & (GV - 1);
+        const int n_mine = min(max(nnzs - base, 0), IPT);
+        T* pv = st.val + (off_v + base);
+#if MSPMV_PIPE_VALS_FIRST
+        // My flag words and values are read BEFORE my gathers are issued: the LSU serves a warp's
+        // shared-memory reads and its 32-sector gathers from one queue, in order, so reads issued after
+        // the gathers would wait behind them (profiles/gather_ceiling_r02.txt).
+        const uint32_t w0 = ctl.bits[bsel][base >> 5], w1 = ctl.bits[bsel][(base >> 5) + 1];
+        T vv[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) vv[j] = j < n_mine ? pv[j] : T(0);
+#endif
         if (C::AHEAD) {
             if (i + 1 < n) {
                 const int sc1 = (i + 1) % CSTAGES;
@@ -314,25 +331,25 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         } else {
             gather(i, cur, xc);
         }
-        const int x0 = cur.x, y0 = cur.y, nrows = cur.z - cur.x, nnzs = cur.w - cur.y;
-        const int off_v = (y0 + shift_v) & (GV - 1);
-        const int n_mine = min(max(nnzs - base, 0), IPT);
 
-        // ---- W: my flag bits, then walk my slots (cpu_spmv.cpp:324-340) ----------------------------
+        // ---- W: walk my slots (cpu_spmv.cpp:324-340) ------------------------------------------------
+#if !MSPMV_PIPE_VALS_FIRST
         const uint32_t w0 = ctl.bits[bsel][base >> 5], w1 = ctl.bits[bsel][(base >> 5) + 1];
+#endif
         const uint32_t bits = __funnelshift_r(w0, w1, base & 31) & ((1u << IPT) - 1u);
         T running = T(0);
-        {
-            T* pv = st.val + (off_v + base);
 #pragma unroll
-            for (int j = 0; j < IPT; ++j) {
-                const T v = j < n_mine ? pv[j] : T(0);
-                if ((bits >> j) & 1u) {  // a row ends in front of slot j: park its sum, start over
-                    pv[j] = running;
-                    running = T(0);
-                }
-                running = fma(v, xc[j], running);
+        for (int j = 0; j < IPT; ++j) {
+#if MSPMV_PIPE_VALS_FIRST
+            const T v = vv[j];
+#else
+            const T v = j < n_mine ? pv[j] : T(0);
+#endif
+            if ((bits >> j) & 1u) {  // a row ends in front of slot j: park its sum, start over
+                pv[j] = running;
+                running = T(0);
             }
+            running = fma(v, xc[j], running);
         }
         // ---- S: block-wide segmented scan of (had a boundary, tail sum) ----------------------------
         Seg<T> elem, excl, total;
