@@ -305,9 +305,11 @@ def main():
                     help="N>1: how the carries travel -- p2p (default): one kernel per rank storing into the peers' "
                          "symmetric memory over NVLink, fused with the fold (csrc/carry_exchange.cuh; 0.330 vs 0.409 ms "
                          "per step at 8 GPUs, profiles/mg_sweep_r02_n8.txt); nccl: one all_gather + fold kernel")
-    ap.add_argument("--e2e-broadcast", action="store_true",
-                    help="N>1 end to end: x crosses PCIe once (rank 0) and is broadcast over NVLink by NCCL, instead of "
-                         "every rank uploading its own copy (default)")
+    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "upload", "broadcast"],
+                    help="N>1 end to end, how x reaches the GPUs -- upload: every rank copies it from its own pinned host "
+                         "buffer over its own PCIe link; broadcast: it crosses PCIe once (rank 0) and NCCL broadcasts it "
+                         "over NVLink; auto (default): both are timed and the faster one is reported as e2e, the other "
+                         "under e2e.alternatives")
     ap.add_argument("--e2e-sequential", action="store_true",
                     help="N>1: run the end-to-end steps one after the other instead of the default three-stream "
                          "pipeline (H2D of x | broadcast + product | D2H of the y slice over three buffer slots)")
@@ -528,91 +530,99 @@ def main():
             #   H2D(i+1) | product + carry exchange (i) | D2H(i-1)      (what mspmv_session_apply_many does at N=1)
             # --e2e-sequential: one step after the other.
             K = 3
-            bcast = bool(args.e2e_broadcast)
-            xh = x.cpu().pin_memory() if (rank == 0 or not bcast) else None
-            s_h2d, s_comp, s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
-            xds = [torch.empty_like(x) for _ in range(K)]
-            yds = [torch.empty(shard.owned_rows, dtype=dt, device=dev) for _ in range(K)]
-            yhs = [torch.empty(shard.owned_rows, dtype=dt).pin_memory() for _ in range(K)]
-            ev_x = [torch.cuda.Event() for _ in range(K)]
-            ev_k = [torch.cuda.Event() for _ in range(K)]
-            ev_y = [torch.cuda.Event() for _ in range(K)]
 
-            # the device part of a slot (sharded CsrMV with its carry exchange, copy into the slot's y buffer) is
-            # captured once per slot: the host then issues one graph launch per step.  With the p2p exchange the
-            # graph holds no NCCL work (the NCCL paths -- --exchange nccl, --e2e-broadcast -- stay eager: replaying
-            # graphs that contain collectives next to eager collectives costs milliseconds per switch)
-            def device_part(sl):
-                if bcast:
-                    dist.broadcast(xds[sl], src=0)
-                yds[sl].copy_(op(xds[sl]))
+            def e2e_variant(bcast):
+                xh = x.cpu().pin_memory() if (rank == 0 or not bcast) else None
+                s_h2d, s_comp, s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
+                xds = [torch.empty_like(x) for _ in range(K)]
+                yds = [torch.empty(shard.owned_rows, dtype=dt, device=dev) for _ in range(K)]
+                yhs = [torch.empty(shard.owned_rows, dtype=dt).pin_memory() for _ in range(K)]
+                ev_x = [torch.cuda.Event() for _ in range(K)]
+                ev_k = [torch.cuda.Event() for _ in range(K)]
+                ev_y = [torch.cuda.Event() for _ in range(K)]
 
-            slot_graphs = []
-            if use_graph and not bcast and args.exchange == "p2p":
-                with torch.cuda.stream(s_comp):
-                    for sl in range(K):
-                        device_part(sl)  # warm-up outside capture
-                s_comp.synchronize()
-                for sl in range(K):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=s_comp):
-                        device_part(sl)
-                    slot_graphs.append(g)
-
-            def run_pipelined(n):
-                for i in range(n):
-                    sl = i % K
-                    with torch.cuda.stream(s_h2d):
-                        if i >= K:
-                            s_h2d.wait_event(ev_k[sl])   # the product that read this x slot is done
-                        if xh is not None:
-                            xds[sl].copy_(xh, non_blocking=True)
-                        ev_x[sl].record(s_h2d)
-                    with torch.cuda.stream(s_comp):
-                        s_comp.wait_event(ev_x[sl])
-                        if i >= K:
-                            s_comp.wait_event(ev_y[sl])  # the copy that drained this y slot is done
-                        if slot_graphs:
-                            slot_graphs[sl].replay()
-                        else:
-                            device_part(sl)
-                        ev_k[sl].record(s_comp)
-                    with torch.cuda.stream(s_d2h):
-                        s_d2h.wait_event(ev_k[sl])
-                        yhs[sl].copy_(yds[sl], non_blocking=True)
-                        ev_y[sl].record(s_d2h)
-                for st in (s_h2d, s_comp, s_d2h):
-                    st.synchronize()
-
-            def run_sequential(n):
-                for i in range(n):
-                    if xh is not None:
-                        xds[0].copy_(xh, non_blocking=True)
+                # the device part of a slot (sharded CsrMV with its carry exchange, copy into the slot's y buffer) is
+                # captured once per slot: the host then issues one graph launch per step.  With the p2p exchange the
+                # graph holds no NCCL work (the NCCL paths -- --exchange nccl, --e2e-broadcast -- stay eager: replaying
+                # graphs that contain collectives next to eager collectives costs milliseconds per switch)
+                def device_part(sl):
                     if bcast:
-                        dist.broadcast(xds[0], src=0)
-                    yhs[0].copy_(op(xds[0]), non_blocking=True)
-                torch.cuda.synchronize()
+                        dist.broadcast(xds[sl], src=0)
+                    yds[sl].copy_(op(xds[sl]))
 
-            run = run_sequential if args.e2e_sequential else run_pipelined
-            torch.cuda.synchronize()
-            run(3 * K)  # warm
-            barrier()
-            t0 = time.perf_counter()
-            run(n_e2e)
-            barrier()
-            dt_s = time.perf_counter() - t0
-            last = yhs[0] if args.e2e_sequential else yhs[(n_e2e - 1) % K]
-            assert torch.equal(last.to(dev), y if not gather_y else y[shard.x0:shard.x1])
-            tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e = {"value": 2.0 * nnz * n_e2e / float(tt.item()) / 1e9, "unit": UNIT,
-                   "h2d_bytes_per_step": cols * vb * (1 if bcast else world), "d2h_bytes_per_step": rows * vb,
-                   "steps": n_e2e,
-                   "api": ("ShardedSpmv: pinned host x on rank 0 -> one H2D -> NCCL broadcast over NVLink" if bcast else
-                           "ShardedSpmv: every rank uploads x from its own pinned host copy over its own PCIe link")
-                          + " -> sharded CsrMV + carry exchange -> every rank's y slice D2H to pinned host memory"
-                          + (", sequential" if args.e2e_sequential else ", three-stream pipeline over 3 slots"),
-                   "bytes_note": "totals over all ranks"}
+                slot_graphs = []
+                if use_graph and not bcast and args.exchange == "p2p":
+                    with torch.cuda.stream(s_comp):
+                        for sl in range(K):
+                            device_part(sl)  # warm-up outside capture
+                    s_comp.synchronize()
+                    for sl in range(K):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=s_comp):
+                            device_part(sl)
+                        slot_graphs.append(g)
+
+                def run_pipelined(n):
+                    for i in range(n):
+                        sl = i % K
+                        with torch.cuda.stream(s_h2d):
+                            if i >= K:
+                                s_h2d.wait_event(ev_k[sl])   # the product that read this x slot is done
+                            if xh is not None:
+                                xds[sl].copy_(xh, non_blocking=True)
+                            ev_x[sl].record(s_h2d)
+                        with torch.cuda.stream(s_comp):
+                            s_comp.wait_event(ev_x[sl])
+                            if i >= K:
+                                s_comp.wait_event(ev_y[sl])  # the copy that drained this y slot is done
+                            if slot_graphs:
+                                slot_graphs[sl].replay()
+                            else:
+                                device_part(sl)
+                            ev_k[sl].record(s_comp)
+                        with torch.cuda.stream(s_d2h):
+                            s_d2h.wait_event(ev_k[sl])
+                            yhs[sl].copy_(yds[sl], non_blocking=True)
+                            ev_y[sl].record(s_d2h)
+                    for st in (s_h2d, s_comp, s_d2h):
+                        st.synchronize()
+
+                def run_sequential(n):
+                    for i in range(n):
+                        if xh is not None:
+                            xds[0].copy_(xh, non_blocking=True)
+                        if bcast:
+                            dist.broadcast(xds[0], src=0)
+                        yhs[0].copy_(op(xds[0]), non_blocking=True)
+                    torch.cuda.synchronize()
+
+                run = run_sequential if args.e2e_sequential else run_pipelined
+                torch.cuda.synchronize()
+                run(3 * K)  # warm
+                barrier()
+                t0 = time.perf_counter()
+                run(n_e2e)
+                barrier()
+                dt_s = time.perf_counter() - t0
+                last = yhs[0] if args.e2e_sequential else yhs[(n_e2e - 1) % K]
+                assert torch.equal(last.to(dev), y if not gather_y else y[shard.x0:shard.x1])
+                tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return {"value": 2.0 * nnz * n_e2e / float(tt.item()) / 1e9, "unit": UNIT,
+                       "h2d_bytes_per_step": cols * vb * (1 if bcast else world), "d2h_bytes_per_step": rows * vb,
+                       "steps": n_e2e,
+                       "api": ("ShardedSpmv: pinned host x on rank 0 -> one H2D -> NCCL broadcast over NVLink" if bcast else
+                               "ShardedSpmv: every rank uploads x from its own pinned host copy over its own PCIe link")
+                              + " -> sharded CsrMV + carry exchange -> every rank's y slice D2H to pinned host memory"
+                              + (", sequential" if args.e2e_sequential else ", three-stream pipeline over 3 slots"),
+                       "bytes_note": "totals over all ranks"}
+
+            modes = {"upload": [False], "broadcast": [True], "auto": [False, True]}[args.e2e_mode]
+            tried = [e2e_variant(b) for b in modes]
+            e2e = max(tried, key=lambda r: r["value"])
+            if len(tried) > 1:
+                e2e["alternatives"] = [{"api": r["api"], "value": r["value"], "h2d_bytes_per_step": r["h2d_bytes_per_step"]}
+                                       for r in tried if r is not e2e]
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------
     cpu = None

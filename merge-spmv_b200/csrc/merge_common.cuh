@@ -184,11 +184,6 @@ __device__ __forceinline__ void block_seg_scan_exclusive(Seg<T> in, Seg<T> carry
     total = run;
 }
 
-// a*b rounded on its own: never contracted with a following add into an FMA, so a product has the
-// same bits whether it is stored first (tile_body) or consumed from a register (tile_body_v3)
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-
 // y = alpha*sum + beta*y_old epilogue (SpmvGold, gpu_spmv.cu:72-92); AXPBY=false is y = sum.
 template <typename T, bool AXPBY>
 __device__ __forceinline__ T epilogue(T sum, T alpha, T beta, const T* y_ptr)

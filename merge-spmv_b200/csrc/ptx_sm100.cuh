@@ -1,6 +1,6 @@
 // ptx_sm100.cuh -- every inline-PTX instruction the sm_100a kernels use, behind one-line wrappers:
-// mbarrier, cp.async.bulk (TMA; SASS UBLKCP / UBLKPF), cp.async (LDGSTS), named barriers, L2 cache
-// policies and the cache-hinted x gathers.  Kernel code contains no asm of its own, so this file is
+// mbarrier, cp.async.bulk (TMA; SASS UBLKCP), the cross-proxy fence, named barriers, L2 cache policies,
+// the cache-hinted x gathers, system-scope stores / loads for the NVLink carry exchange, the global timer.  Kernel code contains no asm of its own, so this file is
 // the complete list of architecture-specific instructions of the library.
 //
 // Test seam: tests/emu/ (a host-side SIMT interpreter used ONLY by the CPU test-suite to run the
@@ -41,37 +41,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Experiment (off = 0): give try_wait a suspend-time hint in nanoseconds, so that a waiting warp stays
-// parked in hardware instead of re-issuing the poll (the poll loop is ~11 % of the tile kernel's
-// executed instructions, which matters where the kernel is issue-bound).
-#ifndef MSPMV_MBAR_SUSPEND_NS
-#define MSPMV_MBAR_SUSPEND_NS 0
-#endif
+// try_wait parks the warp in hardware for a bounded time and returns false when that time is up
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
     do {
-#if MSPMV_MBAR_SUSPEND_NS > 0
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MSPMV_MBAR_SUSPEND_NS)
-            : "memory");
-#else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -79,7 +53,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
-#endif
     } while (!ok);
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
@@ -97,20 +70,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
-}
-// 4- or 8-byte asynchronous global -> shared copy (LDGSTS): the x gather, no register staging
-template <int BYTES>
-__device__ __forceinline__ void cp_async_gather(void* dst_smem, const void* src_gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
-                 "n"(BYTES)
-                 : "memory");
-}
-// arrive on `bar` once all cp.async issued so far by this thread have landed (counted in the
-// barrier's expected arrivals: .noinc)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async()
 {
@@ -147,29 +106,12 @@ __device__ __forceinline__ uint64_t global_timer_ns()
 }
 __device__ __forceinline__ void trap_kernel() { asm volatile("trap;"); }
 
-// L2 prefetch of `bytes` (multiple of 16) at a 16-byte-aligned global address (SASS UBLKPF.L2)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
-
-// x gather: read-only path; do not keep the line in L1 after use (random gathers have no reuse and
-// L1 capacity is what bounds the number of misses in flight -- profiles/microbench_r01.txt); and
-// mark it L2::evict_last while the value / index / row-offset streams are L2::evict_first, so x --
-// the only reused data -- stays L2-resident even when it is tens of MB (profiles/tuning_r01.txt:
-// 20M-column power-law 12.98 -> 5.78 ms).  Flavours: 0 = __ldg, 2 = no_allocate, 3 = + evict_last,
-// 4 = L1-allocating + evict_last, 5 = per-warp choice between 3 and 4 by column span (shipped: a
-// 4096-column-window matrix runs 0.419 ms with 3, 0.273 ms with 4/5; random columns prefer 3).
-#ifndef MSPMV_GATHER_FLAVOUR
-#define MSPMV_GATHER_FLAVOUR 5
-#endif
-// Experiment (off): gathers of scattered columns bypass L1 altogether (ld.global.cg, cached in L2
-// only) instead of ld.global.nc.L1::no_allocate.  The measured gather ceiling depends on how much
-// L1 is left for misses in flight (profiles/microbench_r01.txt); loads that never allocate a line
-// may not be subject to it.
-#ifndef MSPMV_GATHER_SCATTERED_CG
-#define MSPMV_GATHER_SCATTERED_CG 0
-#endif
+// x gathers.  x is the only reused data: every gather carries an L2::evict_last policy while the value /
+// index / row-offset streams are L2::evict_first, so x stays L2-resident even when it is tens of MB
+// (profiles/tuning_r01.txt: 20M-column power-law 12.98 -> 5.78 ms).  Two L1 policies, chosen per warp by
+// the span of its columns: ld_gather for scattered columns (no L1 allocation: random gathers have no reuse,
+// and L1 capacity is what bounds the number of misses in flight -- profiles/microbench_r01.txt), ld_gather_l1
+// for narrow spans (banded / FEM-like locality: lines are re-used).
 __device__ __forceinline__ uint64_t l2_policy_evict_last()
 {
     uint64_t pol;
@@ -179,25 +121,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
 __device__ __forceinline__ float ld_gather(const float* p, uint64_t pol)
 {
     float v;
-#if MSPMV_GATHER_FLAVOUR == 4
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-#elif MSPMV_GATHER_SCATTERED_CG
-    asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-#else
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-#endif
     return v;
 }
 __device__ __forceinline__ double ld_gather(const double* p, uint64_t pol)
 {
     double v;
-#if MSPMV_GATHER_FLAVOUR == 4
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-#elif MSPMV_GATHER_SCATTERED_CG
-    asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-#else
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-#endif
     return v;
 }
 __device__ __forceinline__ float ld_gather_l1(const float* p, uint64_t pol)
@@ -211,26 +141,6 @@ __device__ __forceinline__ double ld_gather_l1(const double* p, uint64_t pol)
     double v;
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
-}
-__device__ __forceinline__ float ld_gather(const float* p)
-{
-#if MSPMV_GATHER_FLAVOUR == 2
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
-__device__ __forceinline__ double ld_gather(const double* p)
-{
-#if MSPMV_GATHER_FLAVOUR == 2
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
 }
 
 }  // namespace mspmv

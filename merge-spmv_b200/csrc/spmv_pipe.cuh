@@ -143,6 +143,39 @@ __device__ __forceinline__ int2 warp_merge_path_search_window(int diag, const in
     return warp_merge_path_search_bounded(diag, row_end_offsets, num_rows, lo, hi, lane);
 }
 
+// Two coordinates over the whole matrix in the SAME rounds (each lane probes one pivot per diagonal per
+// round): the start and the end of a block's first tile cost the dependent L2 trips of one search.
+__device__ __forceinline__ void warp_merge_path_search_global2(int64_t diag_a64, int64_t diag_b64,
+                                                               const int* __restrict__ row_end_offsets, int num_rows,
+                                                               int num_nonzeros, int lane, int2& ca, int2& cb)
+{
+    const int64_t total = (int64_t)num_rows + num_nonzeros;
+    const int da = (int)(diag_a64 < total ? diag_a64 : total), db = (int)(diag_b64 < total ? diag_b64 : total);
+    int lo_a = max(da - num_nonzeros, 0), hi_a = min(da, num_rows);
+    int lo_b = max(db - num_nonzeros, 0), hi_b = min(db, num_rows);
+    while (lo_a < hi_a || lo_b < hi_b) {
+        int piv_a = lo_a + (int)(((int64_t)(hi_a - lo_a) * (lane + 1)) / 33);
+        int piv_b = lo_b + (int)(((int64_t)(hi_b - lo_b) * (lane + 1)) / 33);
+        piv_a = min(piv_a, max(hi_a - 1, lo_a));
+        piv_b = min(piv_b, max(hi_b - 1, lo_b));
+        // a finished search (lo == hi) keeps probing a harmless valid row (or none when the matrix is empty)
+        const bool act_a = lo_a < hi_a, act_b = lo_b < hi_b;
+        const int va = act_a ? __ldg(row_end_offsets + piv_a) : 0;
+        const int vb = act_b ? __ldg(row_end_offsets + piv_b) : 0;
+        const unsigned up_a = __ballot_sync(kFull, act_a && va <= da - piv_a - 1);
+        const unsigned up_b = __ballot_sync(kFull, act_b && vb <= db - piv_b - 1);
+        const int na = __popc(up_a), nb = __popc(up_b);
+        const int a_lo = na > 0 ? __shfl_sync(kFull, piv_a, na - 1) + 1 : lo_a;
+        const int a_hi = na < 32 ? __shfl_sync(kFull, piv_a, na) : hi_a;
+        const int b_lo = nb > 0 ? __shfl_sync(kFull, piv_b, nb - 1) + 1 : lo_b;
+        const int b_hi = nb < 32 ? __shfl_sync(kFull, piv_b, nb) : hi_b;
+        if (act_a) lo_a = a_lo, hi_a = a_hi;
+        if (act_b) lo_b = b_lo, hi_b = b_hi;
+    }
+    ca = make_int2(min(lo_a, num_rows), da - lo_a);
+    cb = make_int2(min(lo_b, num_rows), db - lo_b);
+}
+
 template <class C, bool AXPBY, bool SEARCH>
 __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
     const typename C::value_type* __restrict__ values, const int* __restrict__ row_offsets,
@@ -199,12 +232,14 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
             return warp_merge_path_search_window(d1, row_end, num_rows, max(c.x, d1 - num_nonzeros),
                                                  min(d1 - c.y, num_rows), guess, lane);
         };
-        int2 c0;
-        if (SEARCH)
-            c0 = warp_merge_path_search_global((int64_t)t0 * C::TILE, row_end, num_rows, num_nonzeros, lane);
-        else
+        int2 c0, c1;
+        if (SEARCH) {
+            warp_merge_path_search_global2((int64_t)t0 * C::TILE, (int64_t)(t0 + 1) * C::TILE, row_end, num_rows,
+                                           num_nonzeros, lane, c0, c1);
+        } else {
             c0 = __ldg(coords_in + t0);
-        int2 c1 = next_coord(0, c0, 0);
+            c1 = next_coord(0, c0, 0);
+        }
         for (int i = 0; i < n; ++i) {
             const int s = i % STAGES, sc = i % CSTAGES;
             if (coords_out != nullptr && lane == 0) {

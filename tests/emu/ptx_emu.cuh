@@ -113,11 +113,6 @@ EMU_INTERNAL inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t
     emu_bar(bar)->tx -= (int64_t)bytes;  // complete_tx
     emu_mbar_check_complete(bar);
 }
-inline void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
-{
-    if (((uintptr_t)src_gmem & 15) || (bytes & 15) || bytes == 0)
-        emu::die("cp.async.bulk.prefetch: address must be 16-byte aligned and the size a non-zero multiple of 16");
-}
 inline uint64_t global_timer_ns()
 {
     static uint64_t t = 0;
@@ -144,14 +139,6 @@ EMU_INTERNAL inline uint64_t ld_acquire_sys_u64(const uint64_t* p)
 }
 // cp.async (LDGSTS): the copy is performed at issue; the thread's arrival on the barrier (which the
 // hardware defers until its copies have landed) follows it in program order
-template <int BYTES>
-inline void cp_async_gather(void* dst_smem, const void* src_gmem)
-{
-    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async copies 4, 8 or 16 bytes");
-    if (((uintptr_t)dst_smem | (uintptr_t)src_gmem) & (BYTES - 1)) emu::die("cp.async: misaligned address");
-    std::memcpy(dst_smem, src_gmem, BYTES);
-}
-inline void cp_async_arrive_noinc(uint64_t* bar) { mbar_arrive(bar); }
 inline void fence_proxy_async() {}
 inline void named_bar_sync(int id, int threads) { emu::block_barrier(id, threads); }
 
@@ -168,10 +155,4 @@ inline T ld_gather_l1(const T* p, uint64_t)
 {
     return *p;
 }
-template <typename T>
-inline T ld_gather(const T* p)
-{
-    return *p;
-}
-
 }  // namespace mspmv

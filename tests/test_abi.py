@@ -31,7 +31,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_version_and_error_string():
     L = ms.lib()
-    assert L.mspmv_version() == 1
+    assert L.mspmv_version() == 2  # MSPMV_VERSION_MAJOR * 100 + MINOR (0.2: round 2, pipe engine + mg session)
     assert b"invalid argument" in L.mspmv_error_string(1)
     assert L.mspmv_set_engine(b"bogus") == 1
     assert L.mspmv_set_engine(b"auto") == 0
