@@ -2,10 +2,10 @@
 """Static SASS instruction count per source line of one kernel of libmergespmv.so (built with
 -lineinfo).  Works without a GPU: cuobjdump -xelf + nvdisasm --print-line-info.
 
-    python tools/sass_lines.py spmv_tile_kernelIdLb0        # substring of the mangled kernel name
-    python tools/sass_lines.py spmv_tile3_kernelIdLb0 --by-file
+    python tools/sass_lines.py spmv_pipe_kernelINS_7PipeCfgId        # substring of the mangled kernel name
+    python tools/sass_lines.py spmv_pipe_kernelINS_7PipeCfgIf --by-file
 
-Straight-line kernels like the tile kernel execute most lines once per thread, so the static count
+Straight-line code like the consumer loop of the pipe kernel executes most lines once per thread and tile, so the static count
 is a first estimate of the dynamic one; lines inside uniform branches that are not taken (edge
 cases of the staging helpers, the duplicated L1 / no-L1 gather loop) must be discounted by hand.
 """
@@ -22,9 +22,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def disassemble(lib):
     d = tempfile.mkdtemp(prefix="sass_lines_")
     subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=d, check=True, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    return subprocess.run(["nvdisasm", "--print-line-info", os.path.join(d, cubin)], check=True,
-                          capture_output=True, text=True).stdout.split("\n")
+    out = []
+    for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):  # one per translation unit
+        r = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(d, cubin)], capture_output=True, text=True)
+        if r.returncode == 0:
+            out += r.stdout.split("\n")
+    return out
 
 
 def main():
