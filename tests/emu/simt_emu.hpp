@@ -11,7 +11,7 @@
 // (__syncthreads, named barriers, warp collectives, mbarrier waits).  Blocks run one after another,
 // so `__shared__` variables are plain statics.  A pass over all threads in which nobody made
 // progress is a deadlock (e.g. a barrier not reached by every thread) and aborts with a message.
-// Warp collectives require the full mask -- all the tile engine uses.
+// Warp collectives require the full mask -- all the kernels use.
 #pragma once
 
 #include <cuda_runtime.h>  // vector types; __device__ / __global__ expand to nothing for a host compiler

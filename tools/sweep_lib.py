@@ -9,7 +9,7 @@ it with the CUDA-graph replay bench.py uses.  One line per (workload, option):
     MSPMV_TILE_CARVEOUT=56 python tools/sweep_lib.py --label carve56 --workloads uniform_1m_64,powerlaw_2m
 
 Compile-time switches and the shared-memory carve-out are fixed per process (the library reads the
-carve-out once per kernel); tile_variant / small_fused_tiles are switched at run time.
+carve-out once per kernel); pipe_config / pipe_search are switched at run time.
 """
 import argparse
 import json
@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--label", default="shipped")
     ap.add_argument("--workloads", default="uniform_1m_64,powerlaw_2m,banded_10m,uniform_1m_64_local")
-    ap.add_argument("--options", default="engine=tile;engine=pipe;engine=pipe,pipe_search=0",
+    ap.add_argument("--options", default="engine=pipe;engine=pipe,pipe_search=0",
                     help="semicolon-separated option sets, each a comma-separated list of name=value")
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
