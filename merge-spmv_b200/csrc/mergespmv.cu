@@ -693,6 +693,19 @@ int mspmv_csrmv_config(int value_bytes, int num_rows, int num_nonzeros, int* out
     return value_bytes == 8 ? fill(double()) : fill(float());
 }
 
+#if MSPMV_PIPE_PROFILE
+// tuning builds only (not declared in include/mergespmv.h): per-phase SM cycles of thread 0 of every block
+int mspmv_debug_profile(unsigned long long* out, int reset)
+{
+    if (out) MSPMV_TRY(cudaMemcpyFromSymbol(out, g_pipe_prof, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        MSPMV_TRY(cudaMemcpyToSymbol(g_pipe_prof, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif
+
 const char* mspmv_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
 
 int mspmv_set_engine(const char* name)

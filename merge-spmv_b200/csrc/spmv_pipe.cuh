@@ -49,6 +49,33 @@ namespace mspmv {
 #define MSPMV_PIPE_VALS_FIRST 1
 #endif
 
+// Tuning aid, never in the shipped library (make variants/libmergespmv_prof.so): thread 0 of every block
+// accumulates the SM cycles it spends in each phase of a tile; mspmv_debug_profile() reads the totals.
+#ifndef MSPMV_PIPE_PROFILE
+#define MSPMV_PIPE_PROFILE 0
+#endif
+#if MSPMV_PIPE_PROFILE
+__device__ unsigned long long g_pipe_prof[8];
+__device__ __forceinline__ long long prof_clock()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#define PIPE_PROF_MARK(k)                           \
+    do {                                            \
+        if (tid == 0) {                             \
+            const long long _t = prof_clock();      \
+            prof_acc[k] += _t - prof_last;          \
+            prof_last = _t;                         \
+        }                                           \
+    } while (0)
+#else
+#define PIPE_PROF_MARK(k) \
+    do {                  \
+    } while (0)
+#endif
+
 // Compile-time shape of one kernel instantiation.
 //   IPT     nonzero slots per consumer thread (odd: conflict-free strided shared-memory reads)
 //   VST     slots of the value / row-offset ring      CST   slots of the column-index ring
@@ -340,8 +367,13 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
     named_bar_sync(2, C::CONSUMERS);
 
     // one tile: xc = its x values (AHEAD: gathered one step ago), xn = where the next tile's go
+#if MSPMV_PIPE_PROFILE
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_last = prof_clock();
+#endif
     auto step = [&](int i, T(&xc)[IPT], T(&xn)[IPT]) {
         const int s = i % STAGES, bsel = i & 1;
+        PIPE_PROF_MARK(7);  // loop overhead / between tiles
         PipeStage<C>& st = stages[s];
         const int x0 = cur.x, y0 = cur.y, nrows = cur.z - cur.x, nnzs = cur.w - cur.y;
         const int off_v = (y0 + shift_v) & (GV - 1);
@@ -367,6 +399,7 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
             gather(i, cur, xc);
         }
 
+        PIPE_PROF_MARK(0);  // shared-memory reads issued, column indices read, gathers issued
         // ---- W: walk my slots (cpu_spmv.cpp:324-340) ------------------------------------------------
 #if !MSPMV_PIPE_VALS_FIRST
         const uint32_t w0 = ctl.bits[bsel][base >> 5], w1 = ctl.bits[bsel][(base >> 5) + 1];
@@ -386,6 +419,7 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
             }
             running = fma(v, xc[j], running);
         }
+        PIPE_PROF_MARK(1);  // walk (waits for the gathered x values)
         // ---- S: block-wide segmented scan of (had a boundary, tail sum) ----------------------------
         Seg<T> elem, excl, total;
         elem.val = running;
@@ -395,6 +429,7 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         if (tid < C::BW) ctl.bits[bsel][tid] = 0u;  // everybody read its bits before the scan's barrier
         carry.val = total.val;
 
+        PIPE_PROF_MARK(2);  // scan (one named barrier inside)
         // ---- P1 of the next tile, then the barrier that publishes the parked sums -----------------
         if (i + 1 < n) {
             if (!C::AHEAD) {
@@ -406,7 +441,9 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
             mbar_wait(&ctl.full[s1], (uint32_t)((i + 1) / STAGES) & 1u);
             mark_rows(nxt, stages[s1], ctl.bits[bsel ^ 1]);
         }
+        PIPE_PROF_MARK(3);  // waits for the next tile's data + P1
         named_bar_sync(2, C::CONSUMERS);
+        PIPE_PROF_MARK(4);  // barrier
 
         // ---- Y: row owners store y ----------------------------------------------------------------
         {
@@ -430,6 +467,7 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl.empty[s]);
         cur = nxt;
+        PIPE_PROF_MARK(5);  // Y + release
     };
     if (C::AHEAD) {
         for (int i = 0; i < n; i += 2) {  // ping-pong register sets: no copy waits for the gathers in flight
@@ -440,6 +478,12 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         for (int i = 0; i < n; ++i) step(i, xa, xa);
     }
 
+#if MSPMV_PIPE_PROFILE
+    if (tid == 0) {
+        for (int k = 0; k < 8; ++k) atomicAdd(&g_pipe_prof[k], (unsigned long long)prof_acc[k]);
+        atomicAdd(&g_pipe_prof[6], (unsigned long long)n);  // tiles (slot 6 is not a phase)
+    }
+#endif
     // ---- the run's carry-out; the last block to finish folds all of them (cpu_spmv.cpp:348-352) ---
     if (tid == 0) {
         carry_rows[blockIdx.x] = cur.z;  // may equal num_rows: dropped by the fold
