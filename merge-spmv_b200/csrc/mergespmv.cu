@@ -95,7 +95,7 @@ static int pipe_smem_kb(int cfg)
 
 // Two instantiations of the pipe kernel per value type: A for matrices with long rows (the x gathers
 // dominate), B for short rows (row bookkeeping dominates).  <IPT fp64, IPT fp32, value-ring slots,
-// column-ring slots, gather-ahead, consumer warps>; overridable at build time for tuning sweeps.
+// column-ring slots, gather-ahead, consumer warps, first-segment-in-register>; overridable at build time for tuning sweeps.
 // (nvcc splits -D values at commas, hence one macro per field; PB_* default to PA_*)
 #ifndef PA_I64
 #define PA_I64 11
@@ -115,6 +115,12 @@ static int pipe_smem_kb(int cfg)
 #ifndef PA_NW
 #define PA_NW 4
 #endif
+#ifndef PA_FIR
+#define PA_FIR 1
+#endif
+#ifndef PB_FIR
+#define PB_FIR 0
+#endif
 #ifndef PB_I64
 #define PB_I64 9
 #endif
@@ -133,13 +139,13 @@ static int pipe_smem_kb(int cfg)
 #ifndef PB_NW
 #define PB_NW PA_NW
 #endif
-#define MSPMV_PIPE_A PA_I64, PA_I32, PA_VST, PA_CST, PA_AHEAD, PA_NW
-#define MSPMV_PIPE_B PB_I64, PB_I32, PB_VST, PB_CST, PB_AHEAD, PB_NW
+#define MSPMV_PIPE_A PA_I64, PA_I32, PA_VST, PA_CST, PA_AHEAD, PA_NW, PA_FIR
+#define MSPMV_PIPE_B PB_I64, PB_I32, PB_VST, PB_CST, PB_AHEAD, PB_NW, PB_FIR
 #ifndef MSPMV_PIPE_B_MAX_ROW_ITEMS
 #define MSPMV_PIPE_B_MAX_ROW_ITEMS 16  // B when (rows + nnz) / rows <= this
 #endif
-template <typename T, int I64, int I32, int VST, int CST, int AHEAD, int NW>
-using PipeCfgSel = PipeCfg<T, (sizeof(T) == 8 ? I64 : I32), VST, CST, AHEAD, NW>;
+template <typename T, int I64, int I32, int VST, int CST, int AHEAD, int NW, int FIR>
+using PipeCfgSel = PipeCfg<T, (sizeof(T) == 8 ? I64 : I32), VST, CST, AHEAD, NW, FIR>;
 template <typename T>
 using PipeCfgA = PipeCfgSel<T, MSPMV_PIPE_A>;
 template <typename T>

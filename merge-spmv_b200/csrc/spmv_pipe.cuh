@@ -81,7 +81,11 @@ __device__ __forceinline__ long long prof_clock()
 //   VST     slots of the value / row-offset ring      CST   slots of the column-index ring
 //   AHEAD   1: gathers of tile i+1 are issued before tile i is walked (software pipelining)
 //   NW      consumer warps per block
-template <typename T, int IPT_, int VST_, int CST_, int AHEAD_, int NW_ = 4>
+//   FIR     1: a thread's first finished segment waits in a register for the scan instead of being parked and
+//           patched in shared memory -- one scattered shared-memory read less per thread and tile, a few more
+//           instructions: +3.5 % on the gather-bound power-law config, -10 % on the instruction-bound banded
+//           one (profiles/sweep_r02_switches.txt), hence a property of the shape
+template <typename T, int IPT_, int VST_, int CST_, int AHEAD_, int NW_ = 4, int FIR_ = 0>
 struct PipeCfg {
     using value_type = T;
     static constexpr int NW = NW_;
@@ -92,6 +96,7 @@ struct PipeCfg {
     static constexpr int STAGES = VST_;
     static constexpr int CSTAGES = CST_;
     static constexpr bool AHEAD = AHEAD_ != 0;
+    static constexpr bool FIRST_IN_REG = FIR_ != 0;
     static constexpr int BW = TILE / 32 + 2;        // bitmap words (slot TILE is never flagged; +1 for the funnel shift)
     // row offsets staged per tile (tiles with more rows read them through L2): a third of the tile, at most 384
     static constexpr int ROWCAP = (TILE / 3 < 384 ? ((TILE / 3 + 7) & ~7) : 384);
@@ -405,6 +410,10 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         const uint32_t w0 = ctl.bits[bsel][base >> 5], w1 = ctl.bits[bsel][(base >> 5) + 1];
 #endif
         const uint32_t bits = __funnelshift_r(w0, w1, base & 31) & ((1u << IPT) - 1u);
+        // FIRST_IN_REG: the sum of my first finished segment stays in a register -- it still lacks the partial
+        // that precedes me, which only the scan knows; later segments are complete and are parked right away.
+        const uint32_t first_bit = C::FIRST_IN_REG ? (bits & (0u - bits)) : 0u;  // lowest set flag
+        T first_sum = T(0);
         T running = T(0);
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
@@ -414,7 +423,8 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
             const T v = j < n_mine ? pv[j] : T(0);
 #endif
             if ((bits >> j) & 1u) {  // a row ends in front of slot j: park its sum, start over
-                pv[j] = running;
+                if (C::FIRST_IN_REG && ((first_bit >> j) & 1u)) first_sum = running;
+                else pv[j] = running;
                 running = T(0);
             }
             running = fma(v, xc[j], running);
@@ -425,7 +435,10 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         elem.val = running;
         elem.ended = bits != 0u;
         block_seg_scan_exclusive<T, NW, true>(elem, carry, ctl.warp, tid, 1, excl, total);
-        if (bits != 0u) st.val[off_v + base + (__ffs((int)bits) - 1)] += excl.val;  // my first parked segment
+        if (bits != 0u) {  // my first segment, now complete
+            if (C::FIRST_IN_REG) pv[__ffs((int)bits) - 1] = first_sum + excl.val;
+            else pv[__ffs((int)bits) - 1] += excl.val;
+        }
         if (tid < C::BW) ctl.bits[bsel][tid] = 0u;  // everybody read its bits before the scan's barrier
         carry.val = total.val;
 
@@ -462,7 +475,7 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
                 y[x0 + r] = epilogue<T, AXPBY>(sum, alpha, beta, y + x0 + r);
             }
         }
-        // hand the stage back: my generic-proxy accesses are ordered before the producer's next bulk copy
+        // hand the stage back: my generic-proxy writes into the slot are ordered before the producer's next bulk copy
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl.empty[s]);

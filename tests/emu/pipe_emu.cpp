@@ -21,12 +21,12 @@ int shift_of(const void* p)
     return (int)((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
 }
 
-// kernel shape under test: <IPT fp64, IPT fp32, value-ring slots, column-ring slots, gather-ahead, consumer warps>
+// kernel shape under test: <IPT fp64, IPT fp32, value-ring slots, column-ring slots, gather-ahead, consumer warps, first-in-register>
 #ifndef EMU_PIPE_CFG
-#define EMU_PIPE_CFG 9, 13, 2, 2, 0, 4
+#define EMU_PIPE_CFG 9, 13, 2, 2, 0, 4, 0
 #endif
-template <typename T, int I64, int I32, int VST, int CST, int AHEAD, int NW>
-using CfgSel = PipeCfg<T, (sizeof(T) == 8 ? I64 : I32), VST, CST, AHEAD, NW>;
+template <typename T, int I64, int I32, int VST, int CST, int AHEAD, int NW, int FIR>
+using CfgSel = PipeCfg<T, (sizeof(T) == 8 ? I64 : I32), VST, CST, AHEAD, NW, FIR>;
 
 template <typename T, bool AXPBY>
 int run(const T* values, const int* row_offsets, const int* col, const T* x, T* y, int num_rows, int num_nonzeros,

@@ -22,12 +22,13 @@ from conftest import GOLDEN, ROOT, random_csr
 
 EMU = os.path.join(ROOT, "tests", "emu")
 CSRC = os.path.join(ROOT, "merge-spmv_b200", "csrc")
-VARIANTS = {  # <IPT fp64, IPT fp32, value-ring slots, column-ring slots, gather-ahead, consumer warps>
-    "shipped": [],
-    "ahead_2_2": ["-DEMU_PIPE_CFG=9,13,2,2,1,4"],
-    "ahead_v2_c1_ipt_7_11": ["-DEMU_PIPE_CFG=7,11,2,1,1,4"],
-    "v3_c1_ipt_5_5": ["-DEMU_PIPE_CFG=5,5,3,1,0,4"],
-    "ahead_nw2_v2_c3": ["-DEMU_PIPE_CFG=9,7,2,3,1,2"],
+VARIANTS = {  # <IPT fp64, IPT fp32, value-ring slots, column-ring slots, gather-ahead, consumer warps, first-in-register>
+    "shipped": ["-DEMU_PIPE_CFG=9,13,2,2,0,4,0"],     # shape B of the product (short rows)
+    "shipped_a": ["-DEMU_PIPE_CFG=11,13,2,1,0,4,1"],  # shape A of the product (long rows)
+    "ahead_2_2": ["-DEMU_PIPE_CFG=9,13,2,2,1,4,1"],
+    "ahead_v2_c1_ipt_7_11": ["-DEMU_PIPE_CFG=7,11,2,1,1,4,0"],
+    "v3_c1_ipt_5_5": ["-DEMU_PIPE_CFG=5,5,3,1,0,4,1"],
+    "ahead_nw2_v2_c3": ["-DEMU_PIPE_CFG=9,7,2,3,1,2,0"],
 }
 
 
