@@ -95,7 +95,7 @@ static int pipe_smem_kb(int cfg)
 
 // Two instantiations of the pipe kernel per value type: A for matrices with long rows (the x gathers
 // dominate), B for short rows (row bookkeeping dominates).  <IPT fp64, IPT fp32, value-ring slots,
-// column-ring slots, gather-ahead, consumer warps, first-segment-in-register>; overridable at build time for tuning sweeps.
+// column-ring slots, gather-ahead, consumer warps, first-segment-in-register, values-before-gathers>; overridable at build time for tuning sweeps.
 // (nvcc splits -D values at commas, hence one macro per field; PB_* default to PA_*)
 #ifndef PA_I64
 #define PA_I64 11
@@ -121,6 +121,12 @@ static int pipe_smem_kb(int cfg)
 #ifndef PB_FIR
 #define PB_FIR 0
 #endif
+#ifndef PA_VF
+#define PA_VF 1
+#endif
+#ifndef PB_VF
+#define PB_VF 1
+#endif
 #ifndef PB_I64
 #define PB_I64 9
 #endif
@@ -139,13 +145,13 @@ static int pipe_smem_kb(int cfg)
 #ifndef PB_NW
 #define PB_NW PA_NW
 #endif
-#define MSPMV_PIPE_A PA_I64, PA_I32, PA_VST, PA_CST, PA_AHEAD, PA_NW, PA_FIR
-#define MSPMV_PIPE_B PB_I64, PB_I32, PB_VST, PB_CST, PB_AHEAD, PB_NW, PB_FIR
+#define MSPMV_PIPE_A PA_I64, PA_I32, PA_VST, PA_CST, PA_AHEAD, PA_NW, PA_FIR, PA_VF
+#define MSPMV_PIPE_B PB_I64, PB_I32, PB_VST, PB_CST, PB_AHEAD, PB_NW, PB_FIR, PB_VF
 #ifndef MSPMV_PIPE_B_MAX_ROW_ITEMS
 #define MSPMV_PIPE_B_MAX_ROW_ITEMS 16  // B when (rows + nnz) / rows <= this
 #endif
-template <typename T, int I64, int I32, int VST, int CST, int AHEAD, int NW, int FIR>
-using PipeCfgSel = PipeCfg<T, (sizeof(T) == 8 ? I64 : I32), VST, CST, AHEAD, NW, FIR>;
+template <typename T, int I64, int I32, int VST, int CST, int AHEAD, int NW, int FIR, int VF>
+using PipeCfgSel = PipeCfg<T, (sizeof(T) == 8 ? I64 : I32), VST, CST, AHEAD, NW, FIR, VF>;
 template <typename T>
 using PipeCfgA = PipeCfgSel<T, MSPMV_PIPE_A>;
 template <typename T>

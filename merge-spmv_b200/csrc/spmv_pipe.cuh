@@ -85,7 +85,9 @@ __device__ __forceinline__ long long prof_clock()
 //           patched in shared memory -- one scattered shared-memory read less per thread and tile, a few more
 //           instructions: +3.5 % on the gather-bound power-law config, -10 % on the instruction-bound banded
 //           one (profiles/sweep_r02_switches.txt), hence a property of the shape
-template <typename T, int IPT_, int VST_, int CST_, int AHEAD_, int NW_ = 4, int FIR_ = 0>
+//   VF      1: a thread reads its flag words and values BEFORE it issues its gathers (the LSU serves a warp's
+//           shared-memory reads and its 32-sector gathers from one queue, in order)
+template <typename T, int IPT_, int VST_, int CST_, int AHEAD_, int NW_ = 4, int FIR_ = 0, int VF_ = MSPMV_PIPE_VALS_FIRST>
 struct PipeCfg {
     using value_type = T;
     static constexpr int NW = NW_;
@@ -97,6 +99,7 @@ struct PipeCfg {
     static constexpr int CSTAGES = CST_;
     static constexpr bool AHEAD = AHEAD_ != 0;
     static constexpr bool FIRST_IN_REG = FIR_ != 0;
+    static constexpr bool VALS_FIRST = VF_ != 0;
     static constexpr int BW = TILE / 32 + 2;        // bitmap words (slot TILE is never flagged; +1 for the funnel shift)
     // row offsets staged per tile (tiles with more rows read them through L2): a third of the tile, at most 384
     static constexpr int ROWCAP = (TILE / 3 < 384 ? ((TILE / 3 + 7) & ~7) : 384);
@@ -384,15 +387,17 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         const int off_v = (y0 + shift_v) & (GV - 1);
         const int n_mine = min(max(nnzs - base, 0), IPT);
         T* pv = st.val + (off_v + base);
-#if MSPMV_PIPE_VALS_FIRST
-        // My flag words and values are read BEFORE my gathers are issued: the LSU serves a warp's
-        // shared-memory reads and its 32-sector gathers from one queue, in order, so reads issued after
-        // the gathers would wait behind them (profiles/gather_ceiling_r02.txt).
-        const uint32_t w0 = ctl.bits[bsel][base >> 5], w1 = ctl.bits[bsel][(base >> 5) + 1];
+        // VALS_FIRST: my flag words and values are read BEFORE my gathers are issued -- the LSU serves a warp's
+        // shared-memory reads and its 32-sector gathers from one queue, in order, so reads issued after the
+        // gathers would wait behind them (profiles/gather_ceiling_r02.txt).
+        uint32_t w0 = 0u, w1 = 0u;
         T vv[IPT];
+        if (C::VALS_FIRST) {
+            w0 = ctl.bits[bsel][base >> 5];
+            w1 = ctl.bits[bsel][(base >> 5) + 1];
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) vv[j] = j < n_mine ? pv[j] : T(0);
-#endif
+            for (int j = 0; j < IPT; ++j) vv[j] = j < n_mine ? pv[j] : T(0);
+        }
         if (C::AHEAD) {
             if (i + 1 < n) {
                 const int sc1 = (i + 1) % CSTAGES;
@@ -406,9 +411,10 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
 
         PIPE_PROF_MARK(0);  // shared-memory reads issued, column indices read, gathers issued
         // ---- W: walk my slots (cpu_spmv.cpp:324-340) ------------------------------------------------
-#if !MSPMV_PIPE_VALS_FIRST
-        const uint32_t w0 = ctl.bits[bsel][base >> 5], w1 = ctl.bits[bsel][(base >> 5) + 1];
-#endif
+        if (!C::VALS_FIRST) {
+            w0 = ctl.bits[bsel][base >> 5];
+            w1 = ctl.bits[bsel][(base >> 5) + 1];
+        }
         const uint32_t bits = __funnelshift_r(w0, w1, base & 31) & ((1u << IPT) - 1u);
         // FIRST_IN_REG: the sum of my first finished segment stays in a register -- it still lacks the partial
         // that precedes me, which only the scan knows; later segments are complete and are parked right away.
@@ -417,11 +423,9 @@ __global__ __launch_bounds__(C::THREADS) void spmv_pipe_kernel(
         T running = T(0);
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
-#if MSPMV_PIPE_VALS_FIRST
-            const T v = vv[j];
-#else
-            const T v = j < n_mine ? pv[j] : T(0);
-#endif
+            T v;
+            if (C::VALS_FIRST) v = vv[j];
+            else v = j < n_mine ? pv[j] : T(0);
             if ((bits >> j) & 1u) {  // a row ends in front of slot j: park its sum, start over
                 if (C::FIRST_IN_REG && ((first_bit >> j) & 1u)) first_sum = running;
                 else pv[j] = running;
