@@ -247,6 +247,27 @@ def test_full_size_properties(name):
     assert torch.equal(y4, y1 * 4)
 
 
+def test_config5_full_size_exact():
+    """BASELINE config 5 at full size on one GPU (fp32, 20M x 20M power-law, ~1e9 nonzeros: rows + nnz = 1.02e9,
+    i.e. the int32 merge-path arithmetic near the top of its range): values = x = 1, NaN-poisoned y -- every row
+    must come out as its exact length; twice, bit-identically; and the in-kernel coordinates of the last tiles
+    must reach (rows, nnz) exactly."""
+    set_engine("auto")
+    m = gen.make_config("powerlaw_20m", values="ones", device=DEV)
+    assert m.rows + m.nnz > 1_000_000_000 and m.val.dtype == torch.float32
+    x1 = torch.ones(m.cols, dtype=torch.float32, device=DEV)
+    y = torch.full((m.rows,), float("nan"), dtype=torch.float32, device=DEV)
+    ms.csrmv(m.row_offsets, m.col, m.val, x1, y)
+    lens = torch.diff(m.row_offsets).to(torch.float32)
+    assert torch.equal(y, lens), "config 5: y != row lengths"
+    y2 = torch.full_like(y, float("nan"))
+    ms.csrmv(m.row_offsets, m.col, m.val, x1, y2)
+    assert torch.equal(y, y2)
+    coords = ms.swath_coords(m.row_offsets, 4)
+    assert coords[-1].tolist() == [m.rows, m.nnz] and coords[0].tolist() == [0, 0]
+    assert bool((coords[1:] >= coords[:-1]).all())
+
+
 def test_temp_storage_protocol():
     m = gen.make_config("uniform_1m_64", scale=1 / 64).to(DEV)
     x = torch.ones(m.cols, dtype=torch.float64, device=DEV)
