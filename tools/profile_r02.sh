@@ -4,7 +4,7 @@
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out; mkdir -p "$OUT"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file "$OUT/launches_r02.csv" \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"spmv_pipe|tile_search|carry|diagonal" -c 12 --csv --log-file "$OUT/launches_r02.csv" \
     python bench.py --steps 5 --warmup 3 --graph off --no-cpu-baseline --no-e2e --no-extras > "$OUT/launches_r02.log" 2>&1
 for W in ${WORKLOADS:-uniform_1m_64 banded_10m powerlaw_2m}; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:spmv_pipe -c 1 \
