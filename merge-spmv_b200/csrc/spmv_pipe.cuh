@@ -16,9 +16,9 @@
 //     issued) and the values + row-offset slice (needed until the tile's rows are stored).
 //   * the other warps are the CONSUMERS (all of them compute; no gather/reduce specialisation).
 //     Per tile, with nnzs nonzeros and nrows row ends:
-//       G   every thread owns IPT consecutive nonzero SLOTS: reads its column indices (shared
-//           memory) and issues the x[col] gathers (LDG, cache-hinted) -- with GATHER_AHEAD one tile
-//           ahead of the walk, so the gathers fly while the previous tile is walked and stored;
+//       G   every thread owns IPT consecutive nonzero SLOTS: reads its flag words and values, then its
+//           column indices (shared memory), and issues the x[col] gathers (LDG, cache-hinted) -- with
+//           AHEAD one tile ahead of the walk (a template switch; measured slower, not shipped);
 //       P1  row owners (thread r <-> row r of the tile) set bit (row_end[r] - y0) of a bitmap: a
 //           row boundary lies in front of that slot (slot nnzs = boundary at the tile's end);
 //       W   walk my slots: running = fma(value, x, running); at a flagged slot the finished
@@ -27,8 +27,9 @@
 //           bookkeeping);
 //       S   one warp-shuffle segmented scan of (had a boundary, tail sum) per thread
 //           (ReduceByKeyOp, thread_operators.cuh:278-302) gives every thread the partial that
-//           precedes it -- added to its first parked segment -- and the tile's carry-out, which
-//           stays in registers for the block's next tile;
+//           precedes it -- added to its first finished segment (patched in shared memory, or kept
+//           in a register until now: FIRST_IN_REG) -- and the tile's carry-out, which stays in
+//           registers for the block's next tile;
 //       Y   row owners read their row's parked sum and store y, coalesced (empty rows get 0).
 //     P1 of tile i+1 runs before the barrier that ends S of tile i, so a tile costs two named
 //     barriers among the consumers.
