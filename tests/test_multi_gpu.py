@@ -1,5 +1,7 @@
-"""N>1 on real GPUs: one process per GPU over NCCL (skipped on boxes with a single GPU; the host
-logic of the same path is covered on CPU by tests/test_sharded_gloo.py)."""
+"""N>1 on real GPUs: one process per GPU, both carry exchanges (NCCL all_gather + fold, NVLink peer-memory
+kernel), eagerly and from CUDA graphs (skipped on boxes with a single GPU; the host logic of the same path is
+covered on CPU by tests/test_sharded_gloo.py, the exchange kernel by tests/test_pipe_emu.py; last run on 2 and 8
+GPUs: profiles/mg_sweep_r02_n*.txt)."""
 import os
 import socket
 import sys
@@ -50,27 +52,24 @@ def _worker(rank, world, port, dtype_name, out_dir):
     lens = np.diff(ro)[shard.x0:shard.x1].astype(np.float64)
     tol = 1e-10 if dt == torch.float64 else np.maximum(1e-6, 4 * np.sqrt(lens) * 2.0 ** -24)
     ok_oracle = bool(np.all(np.abs(got - want) <= tol * np.abs(want)))
-    # opt-in: the NVLink peer-memory carry exchange instead of NCCL (not yet run on hardware when written)
-    ok_p2p = True
-    if os.environ.get("MSPMV_TEST_EXPERIMENTAL") == "1":
-        op2 = sharded.ShardedSpmv(shard, exchange="p2p")
-        for _ in range(4):  # several epochs: both parities of the double-buffered slots
-            y2 = op2(x)
-        torch.cuda.synchronize()
-        ok_p2p = torch.equal(y2, y_own)  # same carries, same fold order: same bits
-        rep2 = op2.capture(x)
-        for _ in range(3):
-            y3 = rep2()
-        torch.cuda.synchronize()
-        ok_p2p = ok_p2p and torch.equal(y3, y_own)
-        del rep2
+    # the NVLink peer-memory carry exchange (bench.py's default) instead of NCCL: same carries, same fold
+    # order, so the same bits -- eagerly and replayed from a CUDA graph
+    op2 = sharded.ShardedSpmv(shard, exchange="p2p")
+    for _ in range(4):  # several epochs: both parities of the double-buffered slots
+        y2 = op2(x)
+    torch.cuda.synchronize()
+    ok_p2p = torch.equal(y2, y_own)
+    rep2 = op2.capture(x)
+    for _ in range(3):
+        y3 = rep2()
+    torch.cuda.synchronize()
+    ok_p2p = ok_p2p and torch.equal(y3, y_own)
+    del rep2
     # the y exchange (every rank gets the whole vector), eagerly and replayed from a CUDA graph
     rtol = 1e-5 if dt == torch.float32 else 1e-12
     ok_full = torch.allclose(op.matvec_full(x), full, rtol=rtol, atol=0)
-    replay = None
-    if os.environ.get("MSPMV_TEST_EXPERIMENTAL") == "1":  # graph capture of the y exchange: not yet run on hardware
-        replay = op.capture(x, gather_y=True)
-        ok_full = ok_full and torch.allclose(replay(), full, rtol=rtol, atol=0)
+    replay = op.capture(x, gather_y=True)  # the y exchange replayed from a CUDA graph
+    ok_full = ok_full and torch.allclose(replay(), full, rtol=rtol, atol=0)
     torch.cuda.synchronize()
     flag = torch.tensor([int(ok_local and ok_oracle and ok_full and ok_p2p)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -7,8 +7,8 @@ N=$(nvidia-smi -L 2>/dev/null | wc -l)
 LOG="$OUT/mg_sweep_n$N.txt"; : > "$LOG"
 PY=python
 TR="$PY -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-echo "== $N GPUs: NCCL parity tests (incl. the opt-in p2p exchange and graph capture of the y exchange)" | tee -a "$LOG"
-MSPMV_TEST_EXPERIMENTAL=1 timeout 900 $PY -m pytest tests/test_multi_gpu.py -m gpu -q -x 2>&1 | tail -4 | tee -a "$LOG"
+echo "== $N GPUs: NCCL and NVLink carry exchange parity tests, eager and graph-captured" | tee -a "$LOG"
+timeout 900 $PY -m pytest tests/test_multi_gpu.py -m gpu -q -x 2>&1 | tail -4 | tee -a "$LOG"
 echo "== C-ABI multi-GPU session + C++ driver tests on $N devices" | tee -a "$LOG"
 timeout 900 $PY -m pytest tests -m gpu -q -x -k "mg_session or gpu_driver_self_check" 2>&1 | tail -4 | tee -a "$LOG"
 summ() { $PY -c "
