@@ -10,10 +10,12 @@ same unit the reference's timed loop repeats (gpu_spmv.cu:421-432).  Metric: GFL
 (gpu_spmv.cu:455,463).  At N=1 the default workload is BASELINE.json configs[1]: fp64, 1M x 1M,
 64 nnz/row (826 MB of compulsory traffic per step, larger than the 126 MB L2, so no L2 flush is
 needed between steps).  At N>1 the default is the same family grown with N (weak scaling: N*1M
-rows, one merge-path shard per GPU, one all_gather of N carries per step); fixed-size workloads
-(--workload powerlaw_20m ...) are sharded the same way and reported as "strong".
+rows, one merge-path shard per GPU, one exchange of N carries per step over NVLink); fixed-size
+workloads (--workload powerlaw_20m ...) are sharded the same way and reported as "strong".
 
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  Besides the contract keys it carries `parity` (this run's result against
+an fp64 reference, every rank's rows), `roofline.secondary` (the SM->L2 request-port ceiling that bounds the
+random-column workloads) and `extra_workloads` (BASELINE configs 3 and 4 at N=1, config 5 at every N).
 """
 from __future__ import annotations
 
@@ -298,7 +300,7 @@ def main():
     ap.add_argument("--engine", default=None, choices=[None, "pipe", "auto"])
     ap.add_argument("--cols", type=int, default=None, help="override the column count (x length) of the workload")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay each step (3 kernels, plus the collective and carry fold at N>1) as one CUDA graph; auto = on")
+                    help="replay each step (memset node + the CsrMV kernel, plus the carry exchange at N>1) as one CUDA graph; auto = on")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="mspmv_set_option before the run (e.g. pipe_config=2, pipe_search=0); recorded in config.options")
     ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"],
@@ -525,7 +527,7 @@ def main():
                    "matrix_upload_bytes": int(nnz * (vb + 4) + (rows + 1) * 4)}
         else:
             # N > 1.  Every rank feeds its GPU from its own pinned host copy of x over its own PCIe link and
-            # returns its slice of y to its own pinned host buffer (--e2e-broadcast: x crosses PCIe once, on rank
+            # returns its slice of y to its own pinned host buffer (--e2e-mode broadcast: x crosses PCIe once, on rank
             # 0, and NCCL broadcasts it over NVLink).  Three streams over K slots:
             #   H2D(i+1) | product + carry exchange (i) | D2H(i-1)      (what mspmv_session_apply_many does at N=1)
             # --e2e-sequential: one step after the other.
@@ -543,7 +545,7 @@ def main():
 
                 # the device part of a slot (sharded CsrMV with its carry exchange, copy into the slot's y buffer) is
                 # captured once per slot: the host then issues one graph launch per step.  With the p2p exchange the
-                # graph holds no NCCL work (the NCCL paths -- --exchange nccl, --e2e-broadcast -- stay eager: replaying
+                # graph holds no NCCL work (the NCCL paths -- --exchange nccl, --e2e-mode broadcast -- stay eager: replaying
                 # graphs that contain collectives next to eager collectives costs milliseconds per switch)
                 def device_part(sl):
                     if bcast:
