@@ -423,8 +423,11 @@ def main():
         with sampler:
             if world > 1:
                 # device-side rendezvous right in front of the start event: the ranks leave the host barrier a
-                # few ms apart, and without this the early rank's first step would time the late rank's arrival
+                # few ms apart, and without this the early rank's first step would time the late rank's arrival.
+                # One more untimed step follows it (warm-up W+1): its carry exchange ends at the same moment on
+                # every GPU, which aligns the start events to microseconds where the all-reduce leaves ~10 us.
                 dist.all_reduce(sync_token)
+                step()
             start.record()
             for _ in range(steps):
                 step()
