@@ -32,6 +32,16 @@
 namespace {
 constexpr int kSlots = 3;
 
+// the caller's current device is restored on every exit path
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 struct MgDev {
     int device = 0;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0, local_rows = 0, owned = 0, nnz = 0;
@@ -188,9 +198,8 @@ int mspmv_mg_session_create(mspmv_mg_session** out, int num_shards, const int* d
 
 int mspmv_mg_session_apply_many(mspmv_mg_session* s, int n, const void* xs_host, void* ys_host)
 {
-    if (!s || n < 0) return (int)cudaErrorInvalidValue;
-    int prev = 0;
-    MG_TRY(cudaGetDevice(&prev));
+    if (!s || n < 0 || (n > 0 && (!xs_host || !ys_host))) return (int)cudaErrorInvalidValue;
+    DeviceGuard guard;
     const size_t vb = (size_t)s->value_bytes;
     const size_t xbytes = vb * (size_t)s->cols, ybytes = vb * (size_t)s->rows;
     const char* xs = (const char*)xs_host;
@@ -244,7 +253,6 @@ int mspmv_mg_session_apply_many(mspmv_mg_session* s, int n, const void* xs_host,
         MG_TRY(cudaStreamSynchronize(D.s_compute));
         MG_TRY(cudaStreamSynchronize(D.s_in));
     }
-    MG_TRY(cudaSetDevice(prev));
     return 0;
 }
 
@@ -256,9 +264,8 @@ int mspmv_mg_session_apply(mspmv_mg_session* s, const void* x_host, void* y_host
 int mspmv_mg_session_time_device(mspmv_mg_session* s, int iterations, float* ms_per_step)
 {
     if (!s || iterations < 1 || !ms_per_step) return (int)cudaErrorInvalidValue;
-    int prev = 0;
-    MG_TRY(cudaGetDevice(&prev));
-    const int sl = s->last_slot;
+    DeviceGuard guard;
+    const int sl = s->last_slot;  // the x of the last apply (before any apply: whatever the slot holds -- timing only)
     int rc = mg_launch_products(s, sl);  // warm-up
     if (rc) return rc;
     for (int g = 0; g < s->p; ++g) {
@@ -286,7 +293,6 @@ int mspmv_mg_session_time_device(mspmv_mg_session* s, int iterations, float* ms_
         if (ms > worst) worst = ms;
     }
     *ms_per_step = worst / (float)iterations;
-    MG_TRY(cudaSetDevice(prev));
     return 0;
 }
 
